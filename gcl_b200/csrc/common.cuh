@@ -1,0 +1,133 @@
+// Shared device/host helpers for libgclb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gclb200.h"
+
+namespace gclb {
+
+void set_error(const char* fmt, ...);
+
+#define GCLB_CHECK_ARG(cond, msg)                 \
+  do {                                            \
+    if (!(cond)) {                                \
+      gclb::set_error("%s: %s", __func__, msg);   \
+      return GCLB_ERR_ARG;                        \
+    }                                             \
+  } while (0)
+
+#define GCLB_CHECK_LAUNCH()                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      gclb::set_error("%s: CUDA error: %s", __func__, cudaGetErrorString(e__));          \
+      return GCLB_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- packed coordinate keys: [ batch:10 | x:18 | y:18 | z:18 ], biased by 2^17 ---------------------------
+constexpr int kAxisBits = 18;
+constexpr int kAxisBias = 1 << 17;
+constexpr uint64_t kEmptyKey = ~0ull;  // batch 1023 is reserved for it
+
+__host__ __device__ __forceinline__ bool coord_in_range(int b, int x, int y, int z) {
+  return (unsigned)b < 1023u && (unsigned)(x + kAxisBias) < (1u << kAxisBits) &&
+         (unsigned)(y + kAxisBias) < (1u << kAxisBits) && (unsigned)(z + kAxisBias) < (1u << kAxisBits);
+}
+__host__ __device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z) {
+  return ((uint64_t)(unsigned)b << 54) | ((uint64_t)(unsigned)(x + kAxisBias) << 36) |
+         ((uint64_t)(unsigned)(y + kAxisBias) << 18) | (uint64_t)(unsigned)(z + kAxisBias);
+}
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 fmix64
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+struct HashTable {
+  unsigned long long* keys;
+  int32_t* vals;
+  uint32_t mask;  // capacity - 1
+};
+__host__ __device__ __forceinline__ HashTable make_table(const void* buf, int64_t capacity) {
+  HashTable t;
+  t.keys = (unsigned long long*)buf;
+  t.vals = (int32_t*)((char*)buf + (size_t)capacity * 8);
+  t.mask = (uint32_t)(capacity - 1);
+  return t;
+}
+
+// insert key, value = min(existing, row).  Returns slot, or -1 when the table is full.
+__device__ __forceinline__ int hash_insert_min(const HashTable& t, uint64_t key, int row) {
+  uint32_t slot = hash_key(key) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    unsigned long long prev = t.keys[slot];
+    if (prev == kEmptyKey) prev = atomicCAS(&t.keys[slot], kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey || prev == key) {
+      atomicMin(&t.vals[slot], row);
+      return (int)slot;
+    }
+    slot = (slot + 1) & t.mask;
+  }
+  return -1;
+}
+__device__ __forceinline__ int hash_find(const HashTable& t, uint64_t key) {
+  uint32_t slot = hash_key(key) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    unsigned long long k = __ldg(&t.keys[slot]);
+    if (k == key) return __ldg(&t.vals[slot]);
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & t.mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int floor_div(int a, int s) { return (a >= 0) ? a / s : -((-a + s - 1) / s); }
+
+// ---- ordered stream compaction of N flags (3 tiny launches, deterministic) -------------------------------
+// workspace: int32 block_counts[nblocks+1]
+constexpr int kCompactBlock = 1024;
+inline int64_t compact_blocks(int64_t n) { return (n + kCompactBlock - 1) / kCompactBlock; }
+
+// block-wide exclusive scan of one int per thread (blockDim.x == kCompactBlock); returns exclusive prefix,
+// total in *total.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += n;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += n;
+    }
+    warp_sums[lane] = wi - w;  // exclusive
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  int r = warp_sums[wid] + incl - v;
+  __syncthreads();
+  return r;
+}
+
+// scan of per-block counts by one block: counts[i] <- exclusive prefix; counts[nblocks] <- total; also
+// optionally stores the total as int64.  (defined in hash.cu)
+void launch_scan_block_counts(int32_t* counts, int64_t nblocks, int64_t* total_out, cudaStream_t st);
+
+}  // namespace gclb

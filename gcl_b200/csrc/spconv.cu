@@ -1,0 +1,417 @@
+// K3 (fp32 CUDA-core path): sparse convolution as an output-stationary implicit GEMM.
+//   out[o,:] = act( (sum_k in[nbr[o,k],:] @ W[k]) * scale + shift + residual[o,:] )
+// A CTA owns BM output rows x BN output channels; for every kernel offset that has at least one neighbour in
+// the tile it gathers the BM x BK input slab into shared memory (zeros where nbr < 0), streams the matching
+// BK x BN weight slab and accumulates in registers, so every output row is written exactly once (no
+// atomics, deterministic) with BatchNorm(eval)/bias, residual add and ReLU fused into the store.
+// This path is exact fp32 and also serves dgrad (conv with the transposed table / transposed weights).
+// The tensor-core path (tcgen05 kind::tf32, accumulators in TMEM) lives in spconv_tc.cu.
+#include "common.cuh"
+
+namespace gclb {
+
+struct ConvParams {
+  const float* in0; const float* in1;
+  int c0, c1;
+  const float* W;
+  int K, cout;
+  const int32_t* nbr;
+  const float* scale; const float* shift; const float* residual;
+  int relu;
+  float* out;
+  int64_t n_out;
+};
+
+constexpr int BK = 32;
+constexpr int kConvThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// VEC: channel counts are multiples of 4 (all ResUNet layers) -> 128-bit gathers
+template <int BM, int BN, bool VEC>
+__global__ void __launch_bounds__(kConvThreads) spconv_fwd_f32_kernel(ConvParams p) {
+  constexpr int TX = BN / 4;       // threads along N
+  constexpr int APAD = BM + 4, BPAD = BN + 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);                 // [BK][APAD]   (transposed: channel-major)
+  float* Bs = As + BK * APAD;                                     // [BK][BPAD]
+  int* nbr_s = reinterpret_cast<int*>(Bs + BK * BPAD);            // [BM][K]
+  int* act_k = nbr_s + BM * p.K;                                  // [K] list of active offsets
+  __shared__ int n_act;
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int64_t tile_m = (int64_t)blockIdx.x * BM;
+  const int tile_n = blockIdx.y * BN;
+  const int K = p.K, cin = p.c0 + p.c1;
+
+  // ---- stage the neighbour tile, find which offsets are populated in this tile
+  for (int k = tid; k < K; k += kConvThreads) act_k[k] = 0;
+  __syncthreads();
+  for (int e = tid; e < BM * K; e += kConvThreads) {
+    int64_t o = tile_m + e / K;
+    int v = -1;
+    if (o < p.n_out) v = p.nbr ? __ldg(&p.nbr[tile_m * K + e]) : (int)o;
+    nbr_s[e] = v;
+    if (v >= 0) act_k[e % K] = 1;
+  }
+  __syncthreads();
+  if (tid < 32) {  // warp 0 compacts the flags into an ascending list (keeps the fp32 summation order fixed)
+    int base = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      int k = k0 + tid;
+      int f = (k < K) ? act_k[k] : 0;
+      __syncwarp();
+      unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) act_k[base + __popc(m & ((1u << tid) - 1))] = k;   // base+rank <= k: never clobbers an unread flag
+      base += __popc(m);
+      __syncwarp();
+    }
+    if (tid == 0) n_act = base;
+  }
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nact = n_act;
+  for (int ai = 0; ai < nact; ++ai) {
+    const int k = act_k[ai];
+    const float* Wk = p.W + (size_t)k * cin * p.cout;
+    for (int cs = 0; cs < cin; cs += BK) {
+      // ---- gather A slab: BM rows x BK channels, stored channel-major
+#pragma unroll
+      for (int pass = 0; pass < BM / 32; ++pass) {
+        int r = pass * 32 + tid / 8;
+        int cv = (tid % 8) * 4;
+        int idx = nbr_s[r * K + k];
+        int c = cs + cv;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx >= 0) {
+          if (VEC) {
+            if (c < cin) v = (c < p.c0) ? ld4(p.in0 + (size_t)idx * p.c0 + c) : ld4(p.in1 + (size_t)idx * p.c1 + (c - p.c0));
+          } else {
+            float t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              int cc = c + j;
+              t[j] = (cc < cin) ? ((cc < p.c0) ? __ldg(p.in0 + (size_t)idx * p.c0 + cc)
+                                               : __ldg(p.in1 + (size_t)idx * p.c1 + (cc - p.c0)))
+                                : 0.f;
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+        As[(cv + 0) * APAD + r] = v.x;
+        As[(cv + 1) * APAD + r] = v.y;
+        As[(cv + 2) * APAD + r] = v.z;
+        As[(cv + 3) * APAD + r] = v.w;
+      }
+      // ---- weight slab: BK x BN
+#pragma unroll
+      for (int pass = 0; pass < (BK * BN / 4 + kConvThreads - 1) / kConvThreads; ++pass) {
+        int e = pass * kConvThreads + tid;
+        if (e < BK * BN / 4) {
+          int kk = e / (BN / 4), nv = (e % (BN / 4)) * 4;
+          int c = cs + kk, n = tile_n + nv;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < cin) {
+            const float* src = Wk + (size_t)c * p.cout + n;
+            if (VEC && n + 3 < p.cout) v = ld4(src);
+            else {
+              if (n + 0 < p.cout) v.x = __ldg(src + 0);
+              if (n + 1 < p.cout) v.y = __ldg(src + 1);
+              if (n + 2 < p.cout) v.z = __ldg(src + 2);
+              if (n + 3 < p.cout) v.w = __ldg(src + 3);
+            }
+          }
+          *reinterpret_cast<float4*>(&Bs[kk * BPAD + nv]) = v;
+        }
+      }
+      __syncthreads();
+      const int kmax = min(BK, cin - cs);
+#pragma unroll 8
+      for (int kk = 0; kk < kmax; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(&As[kk * APAD + ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[kk * BPAD + tx * 4]);
+        float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- fused epilogue
+  const int n0 = tile_n + tx * 4;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int n = n0 + j;
+    sc[j] = (p.scale && n < p.cout) ? __ldg(p.scale + n) : 1.f;
+    sh[j] = (p.shift && n < p.cout) ? __ldg(p.shift + n) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t o = tile_m + ty * 4 + i;
+    if (o >= p.n_out) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
+    float* dst = p.out + (size_t)o * p.cout + n0;
+    const float* res = p.residual ? p.residual + (size_t)o * p.cout + n0 : nullptr;
+    if (VEC && n0 + 3 < p.cout) {
+      if (res) { float4 r = ld4(res); v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w; }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < p.cout) {
+          float t = v[j] + (res ? __ldg(res + j) : 0.f);
+          dst[j] = p.relu ? fmaxf(t, 0.f) : t;
+        }
+    }
+  }
+}
+
+// ---- tiny-Cin layers (conv1: Cin = 1, K = 125, Cout = 32): HBM/L2-bound on the neighbour table, not a GEMM.
+// One warp per output row; lanes = output channels; weights in shared memory; the warp reads 32 table entries
+// at a time and walks the populated ones.
+template <int CIN>
+__global__ void __launch_bounds__(256) spconv_fwd_small_cin_kernel(ConvParams p) {
+  extern __shared__ float Ws[];  // [K*CIN][cout]
+  const int K = p.K, cout = p.cout;
+  for (int e = threadIdx.x; e < K * CIN * cout; e += blockDim.x) Ws[e] = __ldg(p.W + e);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t o = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); o < p.n_out; o += (int64_t)gridDim.x * wpb) {
+    for (int n0 = 0; n0 < cout; n0 += 32) {
+      const int n = n0 + lane;
+      float acc = 0.f;
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        int k = k0 + lane;
+        int idx = (k < K) ? (p.nbr ? __ldg(&p.nbr[o * K + k]) : (int)o) : -1;
+        unsigned m = __ballot_sync(0xffffffffu, idx >= 0);
+        while (m) {
+          int src = __ffs(m) - 1;
+          m &= m - 1;
+          int i = __shfl_sync(0xffffffffu, idx, src);
+          int kk = k0 + src;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            float f = __ldg(p.in0 + (size_t)i * CIN + c);
+            if (n < cout) acc = fmaf(f, Ws[(kk * CIN + c) * cout + n], acc);
+          }
+        }
+      }
+      if (n < cout) {
+        float v = acc * (p.scale ? __ldg(p.scale + n) : 1.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
+        if (p.residual) v += __ldg(p.residual + (size_t)o * cout + n);
+        p.out[(size_t)o * cout + n] = p.relu ? fmaxf(v, 0.f) : v;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, bool VEC>
+static cudaError_t launch_f32(const ConvParams& p, cudaStream_t st) {
+  size_t smem = (size_t)(BK * (BM + 4) + BK * (BN + 4)) * 4 + (size_t)(BM * p.K + p.K) * 4;
+  auto kern = spconv_fwd_f32_kernel<BM, BN, VEC>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)((p.n_out + BM - 1) / BM), (unsigned)((p.cout + BN - 1) / BN));
+  kern<<<grid, kConvThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+int spconv_fwd_tc(const ConvParams& p, int64_t n_in, cudaStream_t st);  // spconv_tc.cu; returns GCLB_ERR_UNSUPPORTED if shape not covered
+bool spconv_tc_supported(const ConvParams& p);
+
+// ---- fused pointwise tail: out = l2norm( relu([in0|in1] W1) W2 + bias )
+constexpr int kTailRows = 64;
+__global__ void __launch_bounds__(256) pointwise_tail_kernel(const float* __restrict__ in0, int c0,
+                                                             const float* __restrict__ in1, int c1, int64_t n,
+                                                             const float* __restrict__ W1, int cmid,
+                                                             const float* __restrict__ W2,
+                                                             const float* __restrict__ bias, int cout, int normalize,
+                                                             float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int cin = c0 + c1;
+  float* Xs = sm;                               // [64][cin+1]
+  float* W1s = Xs + kTailRows * (cin + 1);      // [cin][cmid]
+  float* Hs = W1s + cin * cmid;                 // [64][cmid+1]
+  float* W2s = Hs + kTailRows * (cmid + 1);     // [cmid][cout]
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * kTailRows;
+  for (int e = tid; e < cin * cmid; e += 256) W1s[e] = __ldg(W1 + e);
+  for (int e = tid; e < cmid * cout; e += 256) W2s[e] = __ldg(W2 + e);
+  for (int e = tid; e < kTailRows * cin; e += 256) {
+    int r = e / cin, c = e % cin;
+    int64_t o = row0 + r;
+    float v = 0.f;
+    if (o < n) v = (c < c0) ? __ldg(in0 + (size_t)o * c0 + c) : __ldg(in1 + (size_t)o * c1 + (c - c0));
+    Xs[r * (cin + 1) + c] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < kTailRows * cmid; e += 256) {   // hidden = relu(X W1)
+    int r = e / cmid, m = e % cmid;
+    float a = 0.f;
+    for (int c = 0; c < cin; ++c) a = fmaf(Xs[r * (cin + 1) + c], W1s[c * cmid + m], a);
+    Hs[r * (cmid + 1) + m] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  // 4 threads per row, each cout/4 (strided) outputs; row norm by shuffle over the 4 threads
+  const int r = tid / 4, q = tid % 4;
+  const int64_t o = row0 + r;
+  float ss = 0.f;
+  float vals[32];
+  int cnt = 0;
+  for (int nidx = q; nidx < cout && cnt < 32; nidx += 4, ++cnt) {
+    float a = bias ? __ldg(bias + nidx) : 0.f;
+    for (int m = 0; m < cmid; ++m) a = fmaf(Hs[r * (cmid + 1) + m], W2s[m * cout + nidx], a);
+    vals[cnt] = a;
+    ss = fmaf(a, a, ss);
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  float inv = normalize ? 1.f / sqrtf(ss) : 1.f;
+  if (o < n) {
+    cnt = 0;
+    for (int nidx = q; nidx < cout && cnt < 32; nidx += 4, ++cnt)
+      out[(size_t)o * cout + nidx] = normalize ? vals[cnt] / sqrtf(ss) : vals[cnt];
+  }
+  (void)inv;
+}
+
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int64_t total, int c,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift,
+                                                         const float* __restrict__ residual, int relu,
+                                                         float* __restrict__ y) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int ch = (int)(e % c);
+    float v = x[e] * (scale ? __ldg(scale + ch) : 1.f) + (shift ? __ldg(shift + ch) : 0.f);
+    if (residual) v += residual[e];
+    y[e] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+// per-channel sum / sum of squares over rows (training-mode BatchNorm): block partials in fp32 over <= 64 rows,
+// merged into fp64 accumulators.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* sum,
+                                                       double* sumsq) {
+  const int rows_per_block = 256;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = min(n, r0 + rows_per_block);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      float v = x[r * c + ch];
+      s += v;
+      q += (double)v * v;
+    }
+    atomicAdd(&sum[ch], s);
+    atomicAdd(&sumsq[ch], q);
+  }
+}
+
+}  // namespace gclb
+
+using namespace gclb;
+
+extern "C" {
+
+int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
+                    int32_t K, int32_t cout, const int32_t* nbr, const float* scale, const float* shift,
+                    const float* residual, int32_t relu, float* out, int64_t n_out, int32_t algo, void* stream) {
+  GCLB_CHECK_ARG(W && (n_out == 0 || out), "null pointer");
+  GCLB_CHECK_ARG(c0 >= 1 && c1 >= 0 && K >= 1 && cout >= 1, "bad shape");
+  GCLB_CHECK_ARG((c1 == 0) == (in1 == nullptr), "in1 / c1 mismatch");
+  GCLB_CHECK_ARG(nbr || K == 1, "nbr may be NULL only for K == 1");
+  GCLB_CHECK_ARG(n_in == 0 || in0, "null input");
+  GCLB_CHECK_ARG(algo >= 0 && algo <= 2, "algo must be 0, 1 or 2");
+  if (n_out == 0) return GCLB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvParams p{in0, in1, c0, c1, W, K, cout, nbr, scale, shift, residual, relu, out, n_out};
+  const int cin = c0 + c1;
+  cudaError_t e;
+  if (algo != 1 && spconv_tc_supported(p)) return spconv_fwd_tc(p, n_in, st);
+  if (algo == 2) {
+    set_error("gclb_spconv_fwd: shape (cin=%d, cout=%d, K=%d) is not covered by the tcgen05 kernel", cin, cout, K);
+    return GCLB_ERR_UNSUPPORTED;
+  }
+  if (c1 == 0 && cin <= 4 && (size_t)K * cin * cout * 4 <= 96 * 1024) {
+    size_t smem = (size_t)K * cin * cout * 4;
+    auto launch = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int64_t blocks = (n_out + 7) / 8;
+      if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+      kern<<<(unsigned)blocks, 256, smem, st>>>(p);
+    };
+    if (cin == 1) launch(spconv_fwd_small_cin_kernel<1>);
+    else if (cin == 2) launch(spconv_fwd_small_cin_kernel<2>);
+    else if (cin == 3) launch(spconv_fwd_small_cin_kernel<3>);
+    else launch(spconv_fwd_small_cin_kernel<4>);
+    e = cudaGetLastError();
+  } else {
+    bool vec = (c0 % 4 == 0) && (c1 % 4 == 0) && (cout % 4 == 0);
+    if (cout <= 32) e = vec ? launch_f32<128, 32, true>(p, st) : launch_f32<128, 32, false>(p, st);
+    else e = vec ? launch_f32<64, 64, true>(p, st) : launch_f32<64, 64, false>(p, st);
+  }
+  if (e != cudaSuccess) {
+    set_error("gclb_spconv_fwd: CUDA error: %s", cudaGetErrorString(e));
+    return GCLB_ERR_CUDA;
+  }
+  return GCLB_OK;
+}
+
+int gclb_pointwise_tail(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n, const float* W1,
+                        int32_t cmid, const float* W2, const float* bias, int32_t cout, int32_t normalize, float* out,
+                        void* stream) {
+  GCLB_CHECK_ARG(in0 && W1 && W2 && (n == 0 || out), "null pointer");
+  GCLB_CHECK_ARG((c1 == 0) == (in1 == nullptr), "in1 / c1 mismatch");
+  GCLB_CHECK_ARG(cout <= 128, "cout > 128 unsupported");
+  if (n == 0) return GCLB_OK;
+  int cin = c0 + c1;
+  size_t smem = ((size_t)kTailRows * (cin + 1) + (size_t)cin * cmid + (size_t)kTailRows * (cmid + 1) + (size_t)cmid * cout) * 4;
+  GCLB_CHECK_ARG(smem <= 200 * 1024, "tail layer too wide for shared memory");
+  cudaFuncSetAttribute(pointwise_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pointwise_tail_kernel<<<(unsigned)((n + kTailRows - 1) / kTailRows), 256, smem, (cudaStream_t)stream>>>(
+      in0, c0, in1, c1, n, W1, cmid, W2, bias, cout, normalize, out);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                    const float* residual, int32_t relu, float* y, void* stream) {
+  GCLB_CHECK_ARG(c >= 1 && (n == 0 || (x && y)), "bad arguments");
+  if (n == 0) return GCLB_OK;
+  int64_t total = n * c;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  affine_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, total, c, scale, shift, residual, relu, y);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sumsq, void* stream) {
+  GCLB_CHECK_ARG(c >= 1 && sum && sumsq && (n == 0 || x), "bad arguments");
+  if (n == 0) return GCLB_OK;
+  bn_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, sum, sumsq);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+}  // extern "C"

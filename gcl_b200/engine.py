@@ -1,0 +1,103 @@
+"""Fused eval-mode ResUNet forward: the inference hot path (scripts/test_kitti.py:141-154).
+
+The op-by-op MinkowskiEngine surface launches conv, BatchNorm, ReLU, add and cat separately like the reference
+(~75 calls).  In eval mode all of that folds into the convolution kernels:
+    BatchNorm(eval) -> per-channel scale/shift in the conv epilogue,   `out += residual`, ReLU -> epilogue,
+    ME.cat(a, b)    -> two-source gather,   conv1_tr + ReLU + final + bias + L2 normalise -> one pointwise kernel,
+so a forward is 3 strided-map builds, 11 kernel-map builds, 21 sparse-conv launches and 1 tail launch, with one
+host synchronisation (the strided-map row counts).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+
+
+def _fold(conv, norm, device):
+  W = conv.kernel.detach().to(device=device, dtype=torch.float32).contiguous()
+  bn = norm.bn
+  scale = (bn.weight.detach() if bn.weight is not None else 1.0) * torch.rsqrt(bn.running_var.detach() + bn.eps)
+  shift = (bn.bias.detach() if bn.bias is not None else 0.0) - bn.running_mean.detach() * scale
+  return W, scale.to(device).float().contiguous(), shift.to(device).float().contiguous()
+
+
+class ResUNetEngine:
+  """Build from any ResUNet2-family module (reference class or gcl_b200.resunet) holding the trained weights."""
+
+  def __init__(self, model, device="cuda", algo: int = 0):
+    self.device = torch.device(device)
+    self.algo = algo
+    self.normalize = bool(model.normalize_feature)
+    d = self.device
+    self.conv1_ks = model.conv1.kernel_size
+    f = lambda c, n: _fold(c, n, d)
+    self.p = {"conv1": f(model.conv1, model.norm1)}
+    for name in ("block1", "block2", "block3", "block4", "block4_tr", "block3_tr", "block2_tr"):
+      b = getattr(model, name)
+      self.p[name + ".1"] = f(b.conv1, b.norm1)
+      self.p[name + ".2"] = f(b.conv2, b.norm2)
+    for l in (2, 3, 4):
+      self.p[f"conv{l}"] = f(getattr(model, f"conv{l}"), getattr(model, f"norm{l}"))
+      self.p[f"conv{l}_tr"] = f(getattr(model, f"conv{l}_tr"), getattr(model, f"norm{l}_tr"))
+    self.W1 = model.conv1_tr.kernel.detach().to(d).float().contiguous()
+    self.W2 = model.final.kernel.detach().to(d).float().contiguous()
+    self.bias = model.final.bias.detach().to(d).float().reshape(-1).contiguous() if model.final.bias is not None else None
+    self.last_maps = None
+
+  # ---- building blocks
+  def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False):
+    W, sc, sh = self.p[key]
+    return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=self.algo)
+
+  def _block(self, name, x, nbr):
+    n = x.shape[0]
+    t = self._conv(name + ".1", x, nbr, n, relu=True)
+    return self._conv(name + ".2", t, nbr, n, residual=x, relu=True)
+
+  def build_maps(self, cm1: ops.CoordMap):
+    """strided maps + all kernel maps of one forward (cached by the caller for repeated forwards)."""
+    cm2 = ops.stride_map(cm1, 2, sync=False)
+    # the child maps need their parent's row count on the host for launch sizing: one sync per level would
+    # serialise, so build each level from the (worst-case sized) parent and read all counts at once
+    ops.finish_stride_maps([cm2])
+    cm4 = ops.stride_map(cm2, 2, sync=False)
+    ops.finish_stride_maps([cm4])
+    cm8 = ops.stride_map(cm4, 2, sync=False)
+    ops.finish_stride_maps([cm8])
+    cms = {1: cm1, 2: cm2, 4: cm4, 8: cm8}
+    km = {}
+    if self.conv1_ks != 1:
+      km["c1"] = ops.kernel_map(cm1, cm1, self.conv1_ks)
+    for s in (1, 2, 4, 8):
+      km[f"k3s{s}"] = ops.kernel_map(cms[s], cms[s], 3) if not (s == 1 and self.conv1_ks == 3) else km["c1"]
+    for s in (1, 2, 4):
+      km[f"down{s}"] = ops.kernel_map(cms[s], cms[2 * s], 3)
+      km[f"up{s}"] = ops.kernel_map(cms[2 * s], cms[s], 3, transposed=True)
+    return cms, km
+
+  @torch.no_grad()
+  def forward(self, cm1: ops.CoordMap, feats: torch.Tensor, maps=None) -> torch.Tensor:
+    """feats float32 [N, Cin] on the rows of cm1 -> descriptors float32 [N, out] on the same rows."""
+    cms, km = maps if maps is not None else self.build_maps(cm1)
+    self.last_maps = (cms, km)
+    n1, n2, n4, n8 = cms[1].n, cms[2].n, cms[4].n, cms[8].n
+    x = feats.contiguous().float()
+    s1 = self._block("block1", self._conv("conv1", x, km.get("c1"), n1), km["k3s1"])
+    s2 = self._block("block2", self._conv("conv2", s1, km["down1"], n2), km["k3s2"])
+    s4 = self._block("block3", self._conv("conv3", s2, km["down2"], n4), km["k3s4"])
+    s8 = self._block("block4", self._conv("conv4", s4, km["down4"], n8), km["k3s8"])
+    y4 = self._block("block4_tr", self._conv("conv4_tr", s8, km["up4"], n4), km["k3s4"])
+    y2 = self._block("block3_tr", self._conv("conv3_tr", y4, km["up2"], n2, x2=s4), km["k3s2"])
+    y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2), km["k3s1"])
+    return ops.pointwise_tail(y1, s1, self.W1, self.W2, self.bias, normalize=self.normalize)
+
+  @torch.no_grad()
+  def extract(self, xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] = None):
+    """K1 -> K2 -> K3 for a batch of clouds (xyz float32 [P,3] on the device, cloud_ptr int64 [n+1]).
+    Returns (descriptors [V, out], CoordMap, unique_map): row v describes point xyz[unique_map[v]]."""
+    cm1, umap = ops.voxelize(xyz, voxel, cloud_ptr)
+    feats = torch.ones((cm1.n, 1), dtype=torch.float32, device=xyz.device)
+    return self.forward(cm1, feats), cm1, umap

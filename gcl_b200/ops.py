@@ -1,0 +1,251 @@
+"""Tensor-level wrappers over the C ABI (include/gclb200.h).  PyTorch is used for device memory and streams
+only; every computation below is a libgclb200 kernel."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream, require_cuda
+
+
+class CoordMap:
+  """One coordinate map: int32 rows (b,x,y,z) at a tensor stride + its device hash table."""
+  __slots__ = ("coords", "table", "capacity", "n", "tensor_stride")
+
+  def __init__(self, coords, table, capacity, n, tensor_stride):
+    self.coords, self.table, self.capacity, self.n, self.tensor_stride = coords, table, capacity, n, tensor_stride
+
+
+def _new_table(n_rows: int, device) -> Tuple[torch.Tensor, int]:
+  lib = _lib.load()
+  cap = int(lib.gclb_hash_capacity(int(n_rows)))
+  return torch.empty(int(lib.gclb_hash_bytes(cap)), dtype=torch.uint8, device=device), cap
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+  return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=device)
+
+
+def hash_build(coords4: torch.Tensor, tensor_stride: int = 1, check: bool = True) -> CoordMap:
+  """SparseTensor construction (scripts/test_kitti.py:143-148): insert unique rows, row order preserved."""
+  require_cuda(coords4)
+  assert coords4.dtype == torch.int32 and coords4.dim() == 2 and coords4.shape[1] == 4
+  coords4 = coords4.contiguous()
+  n = coords4.shape[0]
+  table, cap = _new_table(n, coords4.device)
+  status = torch.zeros(1, dtype=torch.int32, device=coords4.device)
+  call("gclb_hash_build", ptr(table), cap, ptr(coords4), n, ptr(status), stream())
+  if check:
+    _lib.check_status(status, "SparseTensor coordinates")
+  return CoordMap(coords4, table, cap, n, tensor_stride)
+
+
+def hash_query(cm: CoordMap, q4: torch.Tensor) -> torch.Tensor:
+  require_cuda(q4)
+  q4 = q4.to(torch.int32).contiguous()
+  out = torch.empty(q4.shape[0], dtype=torch.int32, device=q4.device)
+  call("gclb_hash_query", ptr(cm.table), cm.capacity, ptr(q4), q4.shape[0], ptr(out), stream())
+  return out
+
+
+def voxelize(xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] = None, return_inverse=False,
+             check: bool = True):
+  """K1: sparse_quantize(xyz / voxel) + floor().int() + sparse_collate in one pass
+  (lib/complement_data_loader.py:788-789,809-812,1310-1311).
+  xyz float32 [P,3] (all clouds concatenated), cloud_ptr int64 [n_clouds+1] (host or device).
+  Returns (CoordMap of the V unique voxels in first-occurrence order, unique_map int64 [V] [, inverse int32 [P]])."""
+  require_cuda(xyz)
+  assert xyz.dtype == torch.float32 and xyz.dim() == 2 and xyz.shape[1] == 3
+  xyz = xyz.contiguous()
+  P, dev = xyz.shape[0], xyz.device
+  if cloud_ptr is None:
+    cloud_ptr = torch.tensor([0, P], dtype=torch.int64)
+  n_clouds = cloud_ptr.numel() - 1
+  cloud_ptr = cloud_ptr.to(device=dev, dtype=torch.int64).contiguous()
+  lib = _lib.load()
+  table, cap = _new_table(P, dev)
+  coords = torch.empty((P, 4), dtype=torch.int32, device=dev)
+  umap = torch.empty(P, dtype=torch.int64, device=dev)
+  inv = torch.empty(P, dtype=torch.int32, device=dev) if return_inverse else None
+  n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+  status = torch.zeros(1, dtype=torch.int32, device=dev)
+  ws = _workspace(lib.gclb_compact_workspace_bytes(P), dev)
+  call("gclb_voxelize", ptr(xyz), P, ptr(cloud_ptr), n_clouds, float(voxel), ptr(table), cap, ptr(coords), ptr(umap),
+       ptr(inv), ptr(n_out), ptr(status), ptr(ws), stream())
+  if check:
+    _lib.check_status(status, "voxelize")
+  V = int(n_out.item())
+  cm = CoordMap(coords[:V], table, cap, V, 1)
+  return (cm, umap[:V], inv) if return_inverse else (cm, umap[:V])
+
+
+def quantize_rows(rows: torch.Tensor, return_inverse=False):
+  """first-occurrence de-duplication of int32 rows of width 3 or 4 (ME.utils.sparse_quantize on discrete input)."""
+  require_cuda(rows)
+  rows = rows.to(torch.int32).contiguous()
+  P, width, dev = rows.shape[0], rows.shape[1], rows.device
+  lib = _lib.load()
+  table, cap = _new_table(P, dev)
+  coords = torch.empty((P, 4), dtype=torch.int32, device=dev)
+  umap = torch.empty(P, dtype=torch.int64, device=dev)
+  inv = torch.empty(P, dtype=torch.int32, device=dev) if return_inverse else None
+  n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+  status = torch.zeros(1, dtype=torch.int32, device=dev)
+  ws = _workspace(lib.gclb_compact_workspace_bytes(P), dev)
+  call("gclb_quantize_rows", ptr(rows), P, width, ptr(table), cap, ptr(coords), ptr(umap), ptr(inv), ptr(n_out),
+       ptr(status), ptr(ws), stream())
+  _lib.check_status(status, "sparse_quantize")
+  V = int(n_out.item())
+  cm = CoordMap(coords[:V], table, cap, V, 1)
+  return (cm, umap[:V], inv) if return_inverse else (cm, umap[:V])
+
+
+def stride_map(cm: CoordMap, stride: int, return_parent_rows=False, sync: bool = True):
+  """Strided coordinate map: unique(floor(c / S) * S), S = tensor_stride * stride, first-appearance order.
+  With sync=False the row count stays on the device (CoordMap.n is the device int64 tensor) and `coords`
+  keeps its worst-case length; finalize with `finish_stride_maps`."""
+  new_ts = cm.tensor_stride * stride
+  dev = cm.coords.device
+  lib = _lib.load()
+  n_in = cm.n
+  table, cap = _new_table(n_in, dev)
+  coords = torch.empty((n_in, 4), dtype=torch.int32, device=dev)
+  parent = torch.empty(n_in, dtype=torch.int32, device=dev) if return_parent_rows else None
+  n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+  status = torch.zeros(1, dtype=torch.int32, device=dev)
+  ws = _workspace(lib.gclb_compact_workspace_bytes(n_in), dev)
+  call("gclb_stride_map", ptr(cm.coords), n_in, new_ts, ptr(table), cap, ptr(coords), ptr(parent), ptr(n_out),
+       ptr(status), ptr(ws), stream())
+  out = CoordMap(coords, table, cap, n_out, new_ts)
+  if sync:
+    finish_stride_maps([out])
+  return (out, parent) if return_parent_rows else out
+
+
+def finish_stride_maps(maps: Sequence[CoordMap]):
+  """One host read for the row counts of several freshly built strided maps."""
+  counts = torch.cat([m.n for m in maps]).tolist()
+  for m, n in zip(maps, counts):
+    m.n = int(n)
+    m.coords = m.coords[:m.n]
+
+
+def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1, transposed: bool = False,
+               count_pairs: bool = False):
+  """K2 neighbour table nbr int32 [n_out, ksize^3] (see include/gclb200.h).  Forward: offsets scale with the
+  input tensor stride; transposed (A7): out map is the finer one and offsets scale with ITS stride, negated."""
+  K = ksize ** 3
+  dev = out_cm.coords.device
+  nbr = torch.empty((out_cm.n, K), dtype=torch.int32, device=dev)
+  counts = torch.zeros(K, dtype=torch.int32, device=dev) if count_pairs else None
+  step = out_cm.tensor_stride if transposed else in_cm.tensor_stride
+  call("gclb_kmap_build", ptr(in_cm.table), in_cm.capacity, ptr(out_cm.coords), out_cm.n, ksize, step, dilation,
+       -1 if transposed else 1, ptr(nbr), ptr(counts), stream())
+  return (nbr, counts) if count_pairs else nbr
+
+
+def kernel_map_pairs(nbr: torch.Tensor):
+  """ME-style per-offset (in_idx, out_idx) lists, canonical order; returns (in_idx, out_idx, offset_ptr[K+1])."""
+  n_out, K = nbr.shape
+  dev = nbr.device
+  lib = _lib.load()
+  in_idx = torch.empty(max(n_out * K, 1), dtype=torch.int32, device=dev)
+  out_idx = torch.empty(max(n_out * K, 1), dtype=torch.int32, device=dev)
+  off = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+  ws = _workspace(lib.gclb_compact_workspace_bytes(n_out * K), dev)
+  call("gclb_kmap_pairs", ptr(nbr), n_out, K, ptr(in_idx), ptr(out_idx), ptr(off), ptr(ws), stream())
+  total = int(off[-1].item())
+  return in_idx[:total], out_idx[:total], off
+
+
+def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
+               in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
+               out: Optional[torch.Tensor] = None, algo: int = 0) -> torch.Tensor:
+  """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path)."""
+  require_cuda(in0, W, nbr, in1, scale, shift, residual)
+  if W.dim() == 2:
+    W = W.unsqueeze(0)
+  K, cin, cout = W.shape
+  c0 = in0.shape[1]
+  c1 = in1.shape[1] if in1 is not None else 0
+  assert c0 + c1 == cin, f"channel mismatch: {c0}+{c1} vs {cin}"
+  assert in0.dtype == torch.float32 and W.dtype == torch.float32
+  if nbr is not None:
+    assert nbr.dtype == torch.int32 and tuple(nbr.shape) == (n_out, K)
+  if out is None:
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=in0.device)
+  call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
+       ptr(scale), ptr(shift), ptr(residual), int(bool(relu)), ptr(out), n_out, algo, stream())
+  return out
+
+
+def spconv_wgrad(x: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int) -> torch.Tensor:
+  cin, cout = x.shape[1], gout.shape[1]
+  gW = torch.zeros((K, cin, cout), dtype=torch.float32, device=x.device)
+  call("gclb_spconv_wgrad", ptr(x.contiguous()), cin, x.shape[0], ptr(gout.contiguous()), cout, gout.shape[0],
+       ptr(nbr), K, ptr(gW), stream())
+  return gW
+
+
+def pointwise_tail(in0, in1, W1, W2, bias, normalize=True):
+  n = in0.shape[0]
+  c0, c1 = in0.shape[1], (in1.shape[1] if in1 is not None else 0)
+  cmid, cout = W1.shape[-1], W2.shape[-1]
+  out = torch.empty((n, cout), dtype=torch.float32, device=in0.device)
+  call("gclb_pointwise_tail", ptr(in0), c0, ptr(in1), c1, n, ptr(W1.contiguous()), cmid, ptr(W2.contiguous()),
+       ptr(bias), cout, int(bool(normalize)), ptr(out), stream())
+  return out
+
+
+def affine_act(x, scale=None, shift=None, residual=None, relu=False, out=None):
+  x = x.contiguous()
+  if out is None:
+    out = torch.empty_like(x)
+  call("gclb_affine_act", ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
+       ptr(out), stream())
+  return out
+
+
+def nn_search(A: torch.Tensor, B: torch.Tensor, a_ptr=None, b_ptr=None, both=True, algo: int = 0):
+  """K4.  Returns (idx01 int64 [N], d01 float32 [N], idx10, d10) with squared-L2 distances; segment-local indices
+  when a_ptr/b_ptr (int64 [n_pairs+1], host lists or tensors) are given."""
+  require_cuda(A, B)
+  A, B = A.contiguous(), B.contiguous()
+  assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.shape[1] == B.shape[1]
+  dev = A.device
+  N, M, Cd = A.shape[0], B.shape[0], A.shape[1]
+  if a_ptr is None:
+    a_host, b_host = [0, N], [0, M]
+  else:
+    a_host = a_ptr.tolist() if isinstance(a_ptr, torch.Tensor) else list(a_ptr)
+    b_host = b_ptr.tolist() if isinstance(b_ptr, torch.Tensor) else list(b_ptr)
+  n_pairs = len(a_host) - 1
+  max_n = max(a_host[i + 1] - a_host[i] for i in range(n_pairs))
+  max_m = max(b_host[i + 1] - b_host[i] for i in range(n_pairs))
+  a_dev = torch.tensor(a_host, dtype=torch.int64, device=dev)
+  b_dev = torch.tensor(b_host, dtype=torch.int64, device=dev)
+  lib = _lib.load()
+  idx01 = torch.empty(N, dtype=torch.int64, device=dev)
+  d01 = torch.empty(N, dtype=torch.float32, device=dev)
+  idx10 = torch.empty(M, dtype=torch.int64, device=dev) if both else None
+  d10 = torch.empty(M, dtype=torch.float32, device=dev) if both else None
+  ws = _workspace(lib.gclb_nn_workspace_bytes(N, M), dev)
+  call("gclb_nn", ptr(A), ptr(B), Cd, ptr(a_dev), ptr(b_dev), n_pairs, N, M, max_n, max_m, ptr(idx01), ptr(d01),
+       ptr(idx10), ptr(d10), algo, ptr(ws), stream())
+  return idx01, d01, idx10, d10, a_dev, b_dev, ws
+
+
+def mutual_filter(idx01, idx10, a_dev, b_dev, ws=None):
+  dev = idx01.device
+  n_pairs = a_dev.numel() - 1
+  N = idx01.shape[0]
+  lib = _lib.load()
+  pairs = torch.empty((max(N, 1), 2), dtype=torch.int64, device=dev)
+  pair_ptr = torch.zeros(n_pairs + 1, dtype=torch.int64, device=dev)
+  if ws is None:
+    ws = _workspace(lib.gclb_compact_workspace_bytes(N), dev)
+  call("gclb_mutual_filter", ptr(idx01), ptr(idx10), ptr(a_dev), ptr(b_dev), n_pairs, N, ptr(pairs), ptr(pair_ptr),
+       ptr(ws), stream())
+  return pairs, pair_ptr

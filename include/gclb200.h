@@ -1,0 +1,180 @@
+/* gclb200.h -- C ABI of libgclb200.so: the B200-native (sm_100a) replacement for the MinkowskiEngine /
+ * ATen work on the FCGF/GCL feature-extraction + matching hot path of liuQuan98/GCL.
+ *
+ * The reference has no FFI of its own on this path: it calls the un-vendored MinkowskiEngine Python package
+ * (requirements.txt:8) and ATen.  Each entry point below names the reference call site(s) whose native work
+ * it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; gclb_last_error() gives a thread-local message.
+ *  - all buffers are CALLER-ALLOCATED DEVICE pointers (e.g. PyTorch's caching allocator); no hidden
+ *    allocation, no host synchronisation, no host callbacks: every call only enqueues work on `stream`.
+ *    Results whose size is data dependent are written into caller buffers sized for the worst case and the
+ *    count is written to a device int64 the caller reads when it needs it.
+ *  - `stream` is a cudaStream_t passed as void*.
+ *  - coordinates are int32 rows (batch, x, y, z).  Valid range: 0 <= batch < 1023, |x|,|y|,|z| < 2^17;
+ *    rows outside it set bit GCLB_ST_RANGE in the caller's `status` word (device int32, caller-zeroed).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with GCLB_ERR_CUDA.
+ */
+#ifndef GCLB200_H_
+#define GCLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCLB_OK 0
+#define GCLB_ERR_ARG (-1)
+#define GCLB_ERR_CUDA (-2)
+#define GCLB_ERR_UNSUPPORTED (-3)
+
+/* bits of the device status word */
+#define GCLB_ST_RANGE 1      /* a coordinate was outside the packable range */
+#define GCLB_ST_FULL 2       /* hash table full (capacity too small) */
+#define GCLB_ST_DUPLICATE 4  /* gclb_hash_build saw a duplicated coordinate row */
+
+const char* gclb_last_error(void);
+int gclb_version(void);
+/* 1 when the library was built with the tcgen05 (UTCxMMA) convolution / distance kernels */
+int gclb_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Coordinate hash table: open addressing, linear probing, 64-bit packed keys, int32 values (row index).
+ * Layout in the caller's buffer: uint64 keys[capacity] ; int32 vals[capacity].
+ * Replaces ME's CoordinateMapGPU insert/find (SparseTensor construction: scripts/test_kitti.py:143-148,
+ * lib/colocation_trainer.py:843-845, util/misc.py:128).
+ * ---------------------------------------------------------------------------------------------------- */
+int64_t gclb_hash_capacity(int64_t n_rows);           /* power of two >= 2*n_rows, >= 1024 */
+size_t gclb_hash_bytes(int64_t capacity);
+/* insert N unique rows; vals = row index.  Duplicates keep the smallest row index and set GCLB_ST_DUPLICATE. */
+int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64_t n, int32_t* status, void* stream);
+/* rows_out[q] = row index of q4[q] or -1 */
+int gclb_hash_query(const void* table, int64_t capacity, const int32_t* q4, int64_t nq, int32_t* rows_out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K1 voxelisation = ME.utils.sparse_quantize(xyz / voxel, return_index=True) + floor().int() + sparse_collate
+ * (lib/complement_data_loader.py:788-789,809-812,1310-1311; lib/colocation_data_loader.py:379,388,400-401,446).
+ *   xyz        float32 [P,3]   points of all clouds, concatenated
+ *   cloud_ptr  int64 [n_clouds+1]  (device) start row of each cloud in xyz; batch index = cloud number
+ *   voxel      the divisor; the kernel computes floorf(__fdiv_rn(x, voxel)) (== torch fp32 `xyz / voxel`, floor)
+ *   table      hash buffer of gclb_hash_capacity(P) slots; on return maps coordinate -> compacted row
+ *   coords4_out int32 [P,4], unique_map_out int64 [P]: first V rows valid (ascending first-occurrence order)
+ *   inverse_map_out int32 [P] or NULL: compacted row of every input point
+ *   n_out      device int64[1] = V
+ *   workspace  gclb_compact_workspace_bytes(P) bytes
+ * ---------------------------------------------------------------------------------------------------- */
+size_t gclb_compact_workspace_bytes(int64_t n);
+int gclb_voxelize(const float* xyz, int64_t P, const int64_t* cloud_ptr, int32_t n_clouds, float voxel,
+                  void* table, int64_t capacity, int32_t* coords4_out, int64_t* unique_map_out,
+                  int32_t* inverse_map_out, int64_t* n_out, int32_t* status, void* workspace, void* stream);
+/* same de-duplication for already discretised int32 rows of any width in {3,4} (sparse_quantize on ints,
+ * util/misc.py:117-118).  width==3 rows get batch 0. */
+int gclb_quantize_rows(const int32_t* rows, int64_t P, int32_t width, void* table, int64_t capacity,
+                       int32_t* coords4_out, int64_t* unique_map_out, int32_t* inverse_map_out, int64_t* n_out,
+                       int32_t* status, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Strided coordinate map (ME CoordinateManager::stride; model/resunet.py:62-95 stride-2 convolutions):
+ * out = unique(floor(c / new_stride) * new_stride), rows ordered by first appearance in the parent map.
+ *   out_table   hash buffer of gclb_hash_capacity(n_in) slots -> coordinate -> new row
+ *   out_coords4 int32 [n_in,4] (first *n_out rows valid);  parent_row_out int32 [n_in] or NULL: new row of
+ *   each parent row.
+ * ---------------------------------------------------------------------------------------------------- */
+int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, int32_t new_stride, void* out_table,
+                    int64_t out_capacity, int32_t* out_coords4, int32_t* parent_row_out, int64_t* n_out,
+                    int32_t* status, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K2 kernel map in output-stationary form ("neighbour table"):
+ *   nbr[o*K + k] = input row i with coord_in[i] == coord_out[o] + sign * off_k, else -1,
+ *   off_k = ((ix,iy,iz) - ksize/2) * dilation * offset_stride, k = ix + ksize*iy + ksize^2*iz   (odd ksize;
+ *   even ksize: (ix,iy,iz) * dilation * offset_stride).
+ * Forward conv (model/resunet.py:38-95, residual_block.py:23-33): in_table = input map, out_coords = output
+ * map, offset_stride = input tensor stride, sign=+1.  Transposed conv (model/resunet.py:101-134): in_table =
+ * coarse map, out_coords = fine map, offset_stride = fine tensor stride, sign=-1.
+ *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
+ * ---------------------------------------------------------------------------------------------------- */
+int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
+                    int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t* nbr,
+                    int32_t* pair_count, void* stream);
+/* expand a neighbour table into ME-style per-offset pair lists, canonical order (k ascending, out row
+ * ascending): in_idx/out_idx int32 [n_out*K] (first offset_ptr[K] valid), offset_ptr int64 [K+1]. */
+int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_idx, int32_t* out_idx,
+                    int64_t* offset_ptr, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K3 sparse convolution forward, output-stationary implicit GEMM with fused epilogue
+ *   out[o, :] = act( (sum_k sum_c in[nbr[o,k], c] * W[k, c, :]) * scale + shift + residual[o, :] )
+ * Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward (+ MinkowskiBatchNorm in eval mode,
+ * `out += residual`, MEF.relu, ME.cat when fused): model/resunet.py:173-224, model/residual_block.py:37-53.
+ *   in0 [n_in, c0], in1 [n_in, c1] or NULL : the input is the channel concatenation [in0 | in1] (ME.cat fused)
+ *   W  float32 [K, c0+c1, cout]            : ME layout (Appendix A10)
+ *   nbr int32 [n_out, K] or NULL (K==1: identity map, the kernel_size==1 `F.mm` path)
+ *   scale, shift float32 [cout] or NULL    : folded eval-mode BatchNorm / bias
+ *   residual float32 [n_out, cout] or NULL ; relu 0/1
+ *   algo: 0 = auto, 1 = fp32 CUDA-core kernel (exact fp32), 2 = tcgen05 kind::tf32 (fp32 accumulate in TMEM)
+ * ---------------------------------------------------------------------------------------------------- */
+int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
+                    int32_t K, int32_t cout, const int32_t* nbr, const float* scale, const float* shift,
+                    const float* residual, int32_t relu, float* out, int64_t n_out, int32_t algo, void* stream);
+/* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
+int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
+                      const int32_t* nbr, int32_t K, float* gW, void* stream);
+/* pointwise tail of ResUNet: out = l2normalize( relu([in0|in1] W1) W2 + bias )   (model/resunet.py:217-230) */
+int gclb_pointwise_tail(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n, const float* W1,
+                        int32_t cmid, const float* W2, const float* bias, int32_t cout, int32_t normalize,
+                        float* out, void* stream);
+
+/* elementwise helpers for the op-by-op (training) path: y = act(x * scale[c] + shift[c] + residual) */
+int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                    const float* residual, int32_t relu, float* y, void* stream);
+/* training-mode BatchNorm statistics over all rows: sum[c], sumsq[c] as float64 (caller-zeroed) */
+int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sumsq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K4 nearest neighbour in feature space, both directions from one pass, N x M never materialised.
+ * Replaces lib/eval.py:18-48 (find_nn_gpu) + lib/metrics.py:22-29 (pdist) and the two KD-tree queries of
+ * generalization_ETH/evaluate.py:63-77 (calculate_M).  Squared L2 in the direct-difference form
+ * sum_c (a_c - b_c)^2 in fp32, ties -> smallest index.
+ *   A float32 [sum N_p, C], B float32 [sum M_p, C]; a_ptr/b_ptr int64 [n_pairs+1] device segment starts
+ *   (n_pairs independent problems in one launch).  Indices are LOCAL to the segment.
+ *   idx01 int64 [sum N], d01 float32 [sum N] ; idx10 int64 [sum M], d10 float32 [sum M] (idx10/d10 may be NULL)
+ *   workspace: gclb_nn_workspace_bytes(sum N, sum M)
+ * ---------------------------------------------------------------------------------------------------- */
+size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total);
+int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, const int64_t* b_ptr, int32_t n_pairs,
+            int64_t n_total, int64_t m_total, int64_t max_n, int64_t max_m, int64_t* idx01, float* d01,
+            int64_t* idx10, float* d10, int32_t algo, void* workspace, void* stream);
+/* mutual filter (calculate_M): pairs_out int64 [sum N, 2] = (i, idx01[i]) for rows with idx10[idx01[i]] == i,
+ * ascending i inside each segment, segments concatenated; pair_ptr int64 [n_pairs+1] segment starts. */
+int gclb_mutual_filter(const int64_t* idx01, const int64_t* idx10, const int64_t* a_ptr, const int64_t* b_ptr,
+                       int32_t n_pairs, int64_t n_total, int64_t* pairs_out, int64_t* pair_ptr, void* workspace,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K5 GCL group-wise contrastive loss, forward + backward in one call
+ * (lib/colocation_trainer.py:430-535 finest_contrastive_loss, :734-809 location_contrastive_loss).
+ *   F float32 [N, C] (C <= 128);  group_ptr int64 [G+1] CSR over `index`; index int64 [sum group];
+ *   finest_pos int32 [G] position of the finest member inside each group (or NULL: no finest term);
+ *   pos_sel int64 [n_sel] selected groups; sel_hn1, sel_hn2 int64 [n_hn];
+ *   pos_keys_sorted int64 [n_keys] ascending symmetric pair hashes (util/misc.py:29-40), hash seed = N;
+ *   square_loss 0/1;  losses_out float32 [4] = pos, finest, neg, n_valid_neg;
+ *   weights HOST float32[3] = (pos_w, finest_w, neg_w): gradF += d(sum_i w_i * loss_i)/dF  (gradF device float32
+ *   [N, C], caller-zeroed; NULL = forward only)
+ *   workspace: gclb_loss_workspace_bytes(n_sel, n_hn)
+ * ---------------------------------------------------------------------------------------------------- */
+size_t gclb_loss_workspace_bytes(int64_t n_sel, int64_t n_hn);
+int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
+                    const int32_t* finest_pos, const int64_t* pos_sel, int64_t n_sel, const int64_t* sel_hn1,
+                    const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
+                    float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
+                    const float* weights, float* losses_out, float* gradF, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCLB200_H_ */

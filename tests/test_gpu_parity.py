@@ -1,0 +1,384 @@
+"""GPU parity tests: libgclb200 (through the C ABI / the public Python surface) against the CPU oracle on the
+same seeded inputs.  Bit-exact for integer work (voxel indices, hash lookups, kernel maps, NN indices away from
+ties); features within 1e-3 relative (north_star tolerance; fp32 path is held to 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.me_cpu as OME
+from oracle import gcl_loss as oloss
+from oracle import matching as omatch
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL = 1e-3      # north_star: output features within 1e-3 relative (tensor-core path, fp32 accumulate)
+FP32_TOL = 2e-5      # exact-fp32 kernels only differ from the oracle by summation order
+
+
+@pytest.fixture(scope="module")
+def G():
+  import gcl_b200
+  from gcl_b200 import MinkowskiEngine as ME, engine, loss, matching, ops, synth
+  from gcl_b200.resunet import make_models
+
+  class NS:
+    pass
+
+  ns = NS()
+  ns.ME, ns.ops, ns.engine, ns.matching, ns.loss, ns.synth, ns.make_models = ME, ops, engine, matching, loss, synth, make_models
+  ns.dev = torch.device("cuda:0")
+  return ns
+
+
+def _rel(a, b):
+  a, b = a.double().cpu(), b.double().cpu()
+  return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _random_cloud(seed, n=4000, extent=15.0):
+  rng = np.random.RandomState(seed)
+  pts = np.concatenate([rng.uniform(-extent, extent, (n, 2)), rng.normal(0, 0.4, (n, 1))], 1)
+  return pts.astype(np.float32)
+
+
+def _oracle_voxelize(clouds, voxel):
+  cs, sels, base = [], [], 0
+  for x in clouds:
+    t = torch.from_numpy(x)
+    _, sel = OME.utils.sparse_quantize(t / voxel, return_index=True)
+    cs.append(torch.floor(t[sel] / voxel).int())
+    sels.append(sel + base)
+    base += len(x)
+  C, _ = OME.utils.sparse_collate(cs, [torch.ones(len(c), 1) for c in cs])
+  return C, torch.cat(sels)
+
+
+# ----------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("voxel", [0.3, 0.1, 0.05])
+def test_voxelize_bit_exact(G, voxel):
+  clouds = [_random_cloud(1), _random_cloud(2, 2500), np.zeros((0, 3), np.float32), _random_cloud(3, 100)]
+  clouds[0][:50] = clouds[0][50:100]            # exact duplicates
+  clouds[1][:, 0] -= 40.0                       # negative coordinates
+  C_ref, sel_ref = _oracle_voxelize(clouds, voxel)
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(G.dev)
+  ptr = torch.tensor(np.cumsum([0] + [len(c) for c in clouds]), dtype=torch.int64)
+  cm, umap, inv = G.ops.voxelize(xyz, voxel, ptr, return_inverse=True)
+  assert torch.equal(umap.cpu(), sel_ref)
+  assert torch.equal(cm.coords.cpu(), C_ref)
+  # inverse map: every point lands on the row of its voxel
+  assert torch.equal(cm.coords[inv.long()][:, 1:].cpu(), torch.floor(xyz.cpu() / voxel).int())
+  # the voxeliser's table is usable as the coordinate hash
+  assert torch.equal(G.ops.hash_query(cm, cm.coords).cpu(), torch.arange(cm.n, dtype=torch.int32))
+
+
+def test_voxelize_fp32_division_matches_torch(G):
+  # coordinates chosen to sit on voxel boundaries where x/v vs x*(1/v) differ
+  v = 0.3
+  k = np.arange(-2000, 2000, dtype=np.float32)
+  x = np.stack([k * np.float32(v), k * np.float32(v) + 1e-6, -k * np.float32(v)], 1).astype(np.float32)
+  C_ref, sel_ref = _oracle_voxelize([x], v)
+  cm, umap = G.ops.voxelize(torch.from_numpy(x).to(G.dev), v)
+  assert torch.equal(umap.cpu(), sel_ref) and torch.equal(cm.coords.cpu(), C_ref)
+
+
+def test_voxelize_range_error_is_loud(G):
+  from gcl_b200._lib import GclbError
+  x = torch.tensor([[0.0, 0.0, 0.0], [1e9, 0.0, 0.0]], device=G.dev)
+  with pytest.raises(GclbError):
+    G.ops.voxelize(x, 0.3)
+  with pytest.raises(GclbError):
+    G.ops.voxelize(torch.tensor([[float("nan"), 0.0, 0.0]], device=G.dev), 0.3)
+
+
+def test_sparse_quantize_api(G):
+  pts = torch.from_numpy(_random_cloud(5, 3000))
+  for inp in (pts / 0.3, (pts / 0.3).double().numpy(), torch.floor(pts / 0.3).int()):
+    ref = OME.utils.sparse_quantize(inp, return_index=True, return_inverse=True)
+    got = G.ME.utils.sparse_quantize(inp, return_index=True, return_inverse=True)
+    for r, g in zip(ref, got):
+      assert type(r) is type(g)
+      assert np.array_equal(np.asarray(r), np.asarray(g))
+  um = G.ME.utils.sparse_quantize(pts / 0.3, return_maps_only=True)
+  assert torch.equal(um, OME.utils.sparse_quantize(pts / 0.3, return_maps_only=True))
+
+
+def test_hash_build_query_and_duplicates(G):
+  from gcl_b200._lib import GclbError
+  C_ref, _ = _oracle_voxelize([_random_cloud(7)], 0.2)
+  cm = G.ops.hash_build(C_ref.to(G.dev))
+  q = torch.cat([C_ref[::3], C_ref[:50] + torch.tensor([0, 1000, 0, 0], dtype=torch.int32)])
+  want = torch.cat([torch.arange(0, len(C_ref), 3), torch.full((50,), -1)]).int()
+  assert torch.equal(G.ops.hash_query(cm, q.to(G.dev)).cpu(), want)
+  with pytest.raises(GclbError):
+    G.ops.hash_build(torch.cat([C_ref, C_ref[:1]]).to(G.dev))
+  empty = G.ops.hash_build(torch.zeros((0, 4), dtype=torch.int32, device=G.dev))
+  assert G.ops.hash_query(empty, q.to(G.dev)).eq(-1).all()
+
+
+# ----------------------------------------------------------------------------------------------- K2
+def test_stride_maps_and_kernel_maps_bit_exact(G):
+  clouds = [_random_cloud(11, 6000), _random_cloud(12, 3000)]
+  clouds[1][:, :2] -= 25.0
+  C_ref, _ = _oracle_voxelize(clouds, 0.3)
+  cm1 = G.ops.hash_build(C_ref.to(G.dev))
+  ref = {1: C_ref.numpy()}
+  cms = {1: cm1}
+  for s in (2, 4, 8):
+    ref[s] = OME.stride_coords(ref[s // 2], s)
+    cms[s], parent = G.ops.stride_map(cms[s // 2], 2, return_parent_rows=True)
+    assert cms[s].tensor_stride == s
+    assert np.array_equal(cms[s].coords.cpu().numpy(), ref[s])         # same rows in the same (canonical) order
+    lk = OME._Lookup(ref[s])
+    par = ref[s // 2].astype(np.int64).copy()
+    par[:, 1:] = np.floor_divide(par[:, 1:], s) * s
+    assert np.array_equal(parent.cpu().numpy(), lk.query(par))
+  for s in (1, 2, 4, 8):
+    for ks in ((3, 5) if s == 1 else (3,)):
+      want = OME.build_neighbor_table(ref[s], ref[s], OME.kernel_offsets(ks, s))
+      got, cnt = G.ops.kernel_map(cms[s], cms[s], ks, count_pairs=True)
+      assert np.array_equal(got.cpu().numpy(), want)
+      assert np.array_equal(cnt.cpu().numpy(), (want >= 0).sum(0))
+  for s in (1, 2, 4):
+    down = OME.build_neighbor_table(ref[s], ref[2 * s], OME.kernel_offsets(3, s))
+    up = OME.build_neighbor_table(ref[2 * s], ref[s], -OME.kernel_offsets(3, s))
+    assert np.array_equal(G.ops.kernel_map(cms[s], cms[2 * s], 3).cpu().numpy(), down)
+    assert np.array_equal(G.ops.kernel_map(cms[2 * s], cms[s], 3, transposed=True).cpu().numpy(), up)
+    # pair lists (ME layout), canonical order
+    i, o, off = G.ops.kernel_map_pairs(G.ops.kernel_map(cms[s], cms[2 * s], 3))
+    pairs = OME.neighbor_table_to_pairs(down)
+    off = off.tolist()
+    for k, (pi, po) in enumerate(pairs):
+      assert np.array_equal(i[off[k]:off[k + 1]].cpu().numpy(), pi)
+      assert np.array_equal(o[off[k]:off[k + 1]].cpu().numpy(), po)
+
+
+# ----------------------------------------------------------------------------------------------- K3
+CONV_SHAPES = [(1, 32, 5), (32, 32, 3), (32, 64, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (3, 16, 3), (20, 24, 3)]
+
+
+@pytest.mark.parametrize("cin,cout,ks", CONV_SHAPES)
+def test_spconv_fwd_vs_oracle(G, cin, cout, ks):
+  torch.manual_seed(cin * 1000 + cout)
+  C_ref, _ = _oracle_voxelize([_random_cloud(21, 3000, 8.0)], 0.3)
+  n = len(C_ref)
+  nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(ks, 1))
+  x = torch.randn(n, cin)
+  W = torch.randn(ks ** 3, cin, cout) / np.sqrt(cin * ks ** 3)
+  ref = OME.sparse_conv_reference(x, W, nbr, n)
+  nbr_d = torch.from_numpy(nbr).int().to(G.dev)
+  got = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, algo=1)
+  assert _rel(got, ref) < FP32_TOL
+  got = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, algo=0)
+  assert _rel(got, ref) < FEAT_TOL
+  # fused epilogue: scale/shift, residual, relu
+  sc, sh, res = torch.rand(cout) + 0.5, torch.randn(cout), torch.randn(n, cout)
+  ref2 = torch.relu(ref * sc + sh + res)
+  got2 = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, scale=sc.to(G.dev), shift=sh.to(G.dev),
+                          residual=res.to(G.dev), relu=True, algo=1)
+  assert _rel(got2, ref2) < FP32_TOL
+
+
+def test_spconv_two_source_and_pointwise(G):
+  torch.manual_seed(5)
+  C_ref, _ = _oracle_voxelize([_random_cloud(22, 2000, 6.0)], 0.3)
+  n = len(C_ref)
+  nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(3, 1))
+  a, b = torch.randn(n, 64), torch.randn(n, 32)
+  W = torch.randn(27, 96, 64) / 50
+  ref = OME.sparse_conv_reference(torch.cat([a, b], 1), W, nbr, n)
+  got = G.ops.spconv_fwd(a.to(G.dev), W.to(G.dev), torch.from_numpy(nbr).int().to(G.dev), n, in1=b.to(G.dev), algo=1)
+  assert _rel(got, ref) < FP32_TOL
+  W1, W2, bias = torch.randn(96, 64) / 10, torch.randn(64, 32) / 8, torch.randn(32)
+  y = torch.relu(torch.cat([a, b], 1) @ W1) @ W2 + bias
+  ref_t = y / y.norm(dim=1, keepdim=True)
+  got_t = G.ops.pointwise_tail(a.to(G.dev), b.to(G.dev), W1.to(G.dev), W2.to(G.dev), bias.to(G.dev))
+  assert _rel(got_t, ref_t) < FP32_TOL
+  got_mm = G.ops.spconv_fwd(a.to(G.dev), W1[:64].contiguous().to(G.dev), None, n, algo=1)
+  assert _rel(got_mm, a @ W1[:64]) < FP32_TOL
+
+
+def _seed_bn(model):
+  g = torch.Generator().manual_seed(123)
+  for m in model.modules():
+    if isinstance(m, torch.nn.BatchNorm1d):
+      m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+      m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+      m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+      m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+@pytest.fixture(scope="module")
+def net(G):
+  """oracle model + its output on a 2-cloud batch; the CUDA model shares the state_dict."""
+  torch.manual_seed(0)
+  clouds = [G.synth.cast(G.synth.Scene(3, n_boxes=25, extent=35.0), dict(G.synth.NUSCENES, azimuth_steps=300)),
+            _random_cloud(31, 3000, 10.0)]
+  C_ref, _ = _oracle_voxelize(clouds, 0.3)
+  F_in = torch.ones(len(C_ref), 1)
+  om = G.make_models(OME)["ResUNetBN2C"](1, 32, bn_momentum=0.05, conv1_kernel_size=5, normalize_feature=True)
+  _seed_bn(om)
+  om.eval()
+  with torch.no_grad():
+    ref = om(OME.SparseTensor(F_in, coordinates=C_ref)).F
+  return om, clouds, C_ref, F_in, ref
+
+
+def test_resunet_module_path_vs_oracle(G, net):
+  om, clouds, C_ref, F_in, ref = net
+  gm = G.make_models(G.ME)["ResUNetBN2C"](1, 32, bn_momentum=0.05, conv1_kernel_size=5, normalize_feature=True)
+  gm.load_state_dict(om.state_dict())
+  gm = gm.to(G.dev).eval()
+  with torch.no_grad():
+    st = G.ME.SparseTensor(F_in.to(G.dev), coordinates=C_ref.to(G.dev))
+    out = gm(st)
+  assert out.coordinate_map_key == st.coordinate_map_key
+  assert st.coordinate_manager.stats == {"kmap_builds": 11, "stride_builds": 3}
+  assert _rel(out.F, ref) < FEAT_TOL
+
+
+def test_resunet_engine_vs_oracle(G, net):
+  om, clouds, C_ref, F_in, ref = net
+  eng = G.engine.ResUNetEngine(om, device=G.dev)
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(G.dev)
+  ptr = torch.tensor([0, len(clouds[0]), len(clouds[0]) + len(clouds[1])])
+  feats, cm, umap = eng.extract(xyz, 0.3, ptr)
+  assert torch.equal(cm.coords.cpu(), C_ref)
+  rel = _rel(feats, ref)
+  worst = (feats.cpu() - ref).norm(dim=1).max().item()
+  assert rel < FEAT_TOL and worst < 5e-3, (rel, worst)
+  # permutation equivariance: shuffling the input rows permutes the output rows
+  perm = torch.randperm(len(C_ref))
+  cm_p = G.ops.hash_build(C_ref[perm].to(G.dev))
+  feats_p = eng.forward(cm_p, F_in.to(G.dev))
+  assert _rel(feats_p, ref[perm]) < FEAT_TOL
+
+
+def test_training_step_grads_vs_oracle(G):
+  """conv dgrad / wgrad (stride-1, strided, transposed, 1x1) and train-mode BN through a small U-shaped net."""
+  torch.manual_seed(3)
+  C_ref, _ = _oracle_voxelize([_random_cloud(41, 1500, 6.0), _random_cloud(42, 1500, 6.0)], 0.3)
+  F_in = torch.randn(len(C_ref), 3)
+
+  def build(ME):
+    torch.manual_seed(9)
+    return torch.nn.ModuleDict(dict(
+        c1=ME.MinkowskiConvolution(3, 16, kernel_size=3, stride=1, dimension=3), n1=ME.MinkowskiBatchNorm(16),
+        c2=ME.MinkowskiConvolution(16, 32, kernel_size=3, stride=2, dimension=3), n2=ME.MinkowskiBatchNorm(32),
+        c3=ME.MinkowskiConvolution(32, 32, kernel_size=3, stride=1, dimension=3),
+        t2=ME.MinkowskiConvolutionTranspose(32, 16, kernel_size=3, stride=2, dimension=3),
+        f=ME.MinkowskiConvolution(32, 8, kernel_size=1, stride=1, bias=True, dimension=3)))
+
+  def run(ME, net, Fi, Ci):
+    MEF = ME.MinkowskiFunctional
+    x = ME.SparseTensor(Fi, coordinates=Ci)
+    a = MEF.relu(net["n1"](net["c1"](x)))
+    b = MEF.relu(net["n2"](net["c2"](a)))
+    b2 = net["c3"](b)
+    b2 += b
+    u = net["t2"](MEF.relu(b2))
+    return net["f"](ME.cat(u, a)).F
+
+  on = build(OME)
+  gn = build(G.ME)
+  gn.load_state_dict(on.state_dict())
+  gn = gn.to(G.dev)
+  Fo = F_in.clone().requires_grad_(True)
+  Fg = F_in.clone().to(G.dev).requires_grad_(True)
+  yo = run(OME, on, Fo, C_ref)
+  yg = run(G.ME, gn, Fg, C_ref.to(G.dev))
+  assert _rel(yg.detach(), yo.detach()) < 1e-4
+  w = torch.randn_like(yo)
+  (yo * w).sum().backward()
+  (yg * w.to(G.dev)).sum().backward()
+  assert _rel(Fg.grad, Fo.grad) < 1e-4
+  for (k, po), (_, pg) in zip(on.named_parameters(), gn.named_parameters()):
+    assert _rel(pg.grad, po.grad) < 1e-4, k
+  for (k, bo), (_, bg) in zip(on.named_buffers(), gn.named_buffers()):
+    assert _rel(bg.float(), bo.float()) < 1e-5, k
+
+
+# ----------------------------------------------------------------------------------------------- K4
+def _unit(n, c, seed):
+  x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed))
+  return x / x.norm(dim=1, keepdim=True)
+
+
+@pytest.mark.parametrize("n,m,c", [(5000, 5000, 32), (777, 1301, 32), (1, 5, 32), (300, 200, 16), (130, 257, 7)])
+def test_nn_vs_oracle(G, n, m, c):
+  A, B = _unit(n, c, 1), _unit(m, c, 2)
+  ref_i, ref_d = omatch.find_nn(A, B, nn_max_n=500, return_distance=True)
+  got_i, got_d = G.matching.find_nn_gpu(A.to(G.dev), B.to(G.dev), nn_max_n=500, return_distance=True)
+  assert got_i.dtype == torch.int64 and got_i.device.type == "cpu" and got_d.shape == (n, 1)
+  assert torch.allclose(got_d, ref_d, atol=1e-6)
+  bad = got_i != ref_i
+  if bad.any():   # documented exception: near-ties (second-best within fp32 summation noise of the best)
+    margin = omatch.nn_margin(A, B)
+    assert (margin[bad] < 1e-6).all()
+  assert bad.float().mean() < 1e-3
+
+
+def test_mutual_nn_and_batched_segments(G):
+  sizes = [(900, 1100), (0, 50), (640, 0), (1500, 1300)]
+  As = [_unit(n, 32, 10 + i) for i, (n, _) in enumerate(sizes)]
+  Bs = [torch.cat([a[: min(len(a), m) // 2] + 0.01 * _unit(min(len(a), m) // 2, 32, 50 + i),
+                   _unit(m - min(len(a), m) // 2, 32, 90 + i)]) if m else torch.zeros(0, 32)
+        for i, (a, (_, m)) in enumerate(zip(As, sizes))]
+  a_ptr = np.cumsum([0] + [len(a) for a in As]).tolist()
+  b_ptr = np.cumsum([0] + [len(b) for b in Bs]).tolist()
+  pairs, pair_ptr, idx01, idx10 = G.matching.mutual_nn_device(torch.cat(As).to(G.dev), torch.cat(Bs).to(G.dev), a_ptr, b_ptr)
+  pp = pair_ptr.tolist()
+  for s, (a, b) in enumerate(zip(As, Bs)):
+    got = pairs[pp[s]:pp[s + 1]].cpu().numpy()
+    if len(a) == 0 or len(b) == 0:
+      assert len(got) == 0
+      continue
+    want, nn01, nn10 = omatch.mutual_nn(a, b)
+    assert np.array_equal(idx01[a_ptr[s]:a_ptr[s + 1]].cpu().numpy(), nn01)
+    assert np.array_equal(idx10[b_ptr[s]:b_ptr[s + 1]].cpu().numpy(), nn10)
+    assert np.array_equal(got, want)
+  single = G.matching.mutual_nn(As[0].numpy(), Bs[0].numpy())
+  assert np.array_equal(single, omatch.mutual_nn(As[0], Bs[0])[0])
+
+
+# ----------------------------------------------------------------------------------------------- K5
+def _loss_inputs(seed, N=6000, G_=900, C=32):
+  rng = np.random.RandomState(seed)
+  F = _unit(N, C, seed)
+  sizes = rng.randint(2, 8, G_)
+  index = np.concatenate([rng.choice(N, s, replace=False) for s in sizes]).astype(np.int64)
+  starts = np.concatenate([[0], np.cumsum(sizes)])
+  flag = np.zeros(len(index), bool)
+  flag[starts[:-1] + np.array([rng.randint(0, s) for s in sizes])] = True
+  # make positives somewhat close so both active and inactive hinge branches occur
+  for g in range(G_):
+    members = index[starts[g]:starts[g + 1]]
+    F[members] = F[members[0]] + 0.25 * rng.rand() * torch.randn(len(members), C, generator=torch.Generator().manual_seed(g))
+  F = F / F.norm(dim=1, keepdim=True)
+  ih = oloss.exhaustive_hash([index[starts[g]:starts[g + 1]] for g in range(G_)], N)
+  return F, sizes, index, flag, ih
+
+
+@pytest.mark.parametrize("square,finest", [(True, True), (False, True), (False, False)])
+def test_group_loss_fwd_bwd_vs_oracle(G, square, finest):
+  F, sizes, index, flag, ih = _loss_inputs(7)
+  N = len(F)
+  rng = np.random.RandomState(0)
+  sel = oloss.draw_selections(len(sizes), N, 512, 1024, rng)
+  Fo = F.clone().requires_grad_(True)
+  po, fo, no = oloss.group_contrastive_loss(Fo, sizes, index, ih, flag, *sel, square_loss=square, with_finest=finest)
+  w = (1.0, 0.7 if finest else 0.0, 1.3)
+  (w[0] * po + w[1] * fo + w[2] * no).backward()
+  crit = G.loss.GroupContrastiveLoss(square_loss=square, pos_weight=w[0], finest_weight=w[1], neg_weight=w[2],
+                                     rng=np.random.RandomState(0))
+  Fg = F.clone().to(G.dev).requires_grad_(True)
+  fn = crit.finest_contrastive_loss if finest else crit.location_contrastive_loss
+  if not finest:
+    crit.square_loss = False
+  pg, fg, ng = fn(Fg, torch.from_numpy(sizes), torch.from_numpy(index), ih, torch.from_numpy(flag),
+                  max_pos_cluster=512, max_hn_samples=1024)
+  (w[0] * pg + w[1] * fg + w[2] * ng).backward()
+  assert abs(pg.item() - po.item()) < 1e-5 * max(1, abs(po.item()))
+  assert abs(fg.item() - fo.item()) < 1e-5 * max(1, abs(fo.item()))
+  assert abs(ng.item() - no.item()) < 1e-5 * max(1, abs(no.item()))
+  assert po.item() > 0 and no.item() > 0
+  assert _rel(Fg.grad, Fo.grad) < 1e-4
