@@ -16,6 +16,7 @@ _p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_siz
 SIGNATURES = {
     "gclb_last_error": (C.c_char_p, []),
     "gclb_version": (C.c_int, []),
+    "gclb_kernel_launches": (_i64, []),
     "gclb_has_tcgen05": (C.c_int, []),
     "gclb_hash_capacity": (_i64, [_i64]),
     "gclb_hash_bytes": (_sz, [_i64]),

@@ -9,6 +9,7 @@
 namespace gclb {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // process-wide tally of kernels enqueued by this library (gclb_kernel_launches)
 
 #define GCLB_CHECK_ARG(cond, msg)                 \
   do {                                            \

@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 constexpr int kValInit = 0x7f7f7f7f;
 
 // ------------------------------------------------------------------------------------------------------------
@@ -174,6 +177,7 @@ static int dedupe_rows(Src src, int64_t n, void* table, int64_t capacity, int32_
   scatter_winners_kernel<Src><<<(unsigned)nb, kCompactBlock, 0, st>>>(src, n, t, slot_of, counts, coords4_out,
                                                                       unique_map_out);
   if (inverse_out) inverse_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, t, slot_of, inverse_out);
+  count_launches(inverse_out ? 5 : 4);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -213,6 +217,7 @@ extern "C" {
 
 const char* gclb_last_error(void) { return g_err; }
 int gclb_version(void) { return 100; }
+int64_t gclb_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int64_t gclb_hash_capacity(int64_t n_rows) {
   int64_t c = 1024;
@@ -232,7 +237,7 @@ int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64
   HashTable t = make_table(table, capacity);
   cudaMemsetAsync(t.keys, 0xff, (size_t)capacity * 8, st);
   cudaMemsetAsync(t.vals, 0x7f, (size_t)capacity * 4, st);
-  if (n > 0) hash_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(coords4, n, t, status);
+  if (n > 0) { hash_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(coords4, n, t, status); count_launches(1); }
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -241,6 +246,7 @@ int gclb_hash_query(const void* table, int64_t capacity, const int32_t* q4, int6
                     void* stream) {
   GCLB_CHECK_ARG(table && (nq == 0 || (q4 && rows_out)), "null pointer");
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0, "bad capacity");
+  if (nq > 0) count_launches(1);
   if (nq > 0)
     hash_query_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_table(table, capacity), q4,
                                                                                      nq, rows_out);

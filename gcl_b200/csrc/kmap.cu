@@ -87,6 +87,7 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
       make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, nbr, pair_count);
+  count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -108,6 +109,7 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
   kmap_count_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, K, counts);
   launch_scan_block_counts(counts, nb, nullptr, st);
   kmap_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, K, counts, in_idx, out_idx, offset_ptr);
+  count_launches(3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

@@ -232,6 +232,7 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
   hardneg_kernel<<<(unsigned)((n_hn + 7) / 8), 256, 0, st>>>(p);
   loss_finalize_kernel<<<1, 1024, 0, st>>>(p);
   if (gradF) hardneg_bwd_kernel<<<(unsigned)((n_hn + 7) / 8), 256, 0, st>>>(p);
+  count_launches(gradF ? 4 : 3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

@@ -251,8 +251,10 @@ int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, con
       GCLB_CHECK_ARG(grid.y <= 65535, "too many row tiles");
       if (C % 4 == 0) nn_tile_kernel<true><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, rowbest, colbest);
       else nn_tile_kernel<false><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, rowbest, colbest);
+      count_launches(1);
     }
   }
+  count_launches((n_total > 0) + (idx10 && m_total > 0));
   if (n_total > 0) nn_unpack_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(rowbest, n_total, idx01, d01);
   if (idx10 && m_total > 0)
     nn_unpack_kernel<<<(unsigned)((m_total + 255) / 256), 256, 0, st>>>(colbest, m_total, idx10, d10);
@@ -277,6 +279,7 @@ int gclb_mutual_filter(const int64_t* idx01, const int64_t* idx10, const int64_t
   launch_scan_block_counts(counts, nb, nullptr, st);
   mutual_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(idx01, idx10, a_ptr, b_ptr, n_pairs, n_total, counts,
                                                                 pairs_out, pair_ptr);
+  count_launches(3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

@@ -374,6 +374,7 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
     set_error("gclb_spconv_fwd: CUDA error: %s", cudaGetErrorString(e));
     return GCLB_ERR_CUDA;
   }
+  count_launches(1);
   return GCLB_OK;
 }
 
@@ -390,6 +391,7 @@ int gclb_pointwise_tail(const float* in0, int32_t c0, const float* in1, int32_t 
   cudaFuncSetAttribute(pointwise_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   pointwise_tail_kernel<<<(unsigned)((n + kTailRows - 1) / kTailRows), 256, smem, (cudaStream_t)stream>>>(
       in0, c0, in1, c1, n, W1, cmid, W2, bias, cout, normalize, out);
+  count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -402,6 +404,7 @@ int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, co
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
   affine_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, total, c, scale, shift, residual, relu, y);
+  count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -410,6 +413,7 @@ int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sum
   GCLB_CHECK_ARG(c >= 1 && sum && sumsq && (n == 0 || x), "bad arguments");
   if (n == 0) return GCLB_OK;
   bn_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, sum, sumsq);
+  count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

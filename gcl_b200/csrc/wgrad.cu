@@ -118,6 +118,7 @@ extern "C" int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, con
   dim3 grid((unsigned)((n_out + WCHUNK - 1) / WCHUNK), (unsigned)K,
             (unsigned)(((cin + WT - 1) / WT) * ((cout + WT - 1) / WT)));
   spconv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, cin, gout, cout, n_out, nbr, K, gW);
+  count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

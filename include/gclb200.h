@@ -38,6 +38,8 @@ extern "C" {
 
 const char* gclb_last_error(void);
 int gclb_version(void);
+/* process-wide count of CUDA kernels this library has enqueued so far (bench.py reports the delta) */
+int64_t gclb_kernel_launches(void);
 /* 1 when the library was built with the tcgen05 (UTCxMMA) convolution / distance kernels */
 int gclb_has_tcgen05(void);
 
