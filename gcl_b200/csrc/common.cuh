@@ -30,6 +30,18 @@ void count_launches(int n);   // process-wide tally of kernels enqueued by this 
 
 constexpr int kNumSMs = 148;  // B200
 
+struct ConvParams {   // sparse-conv forward arguments shared by the fp32 (spconv.cu) and tcgen05 (spconv_tc.cu) kernels
+  const float* in0; const float* in1;
+  int c0, c1;
+  const float* W;     // fp32 path: [K][cin][cout] ; tcgen05 path: [K][cout][cin] (gclb_weights_to_tc)
+  int K, cout;
+  const int32_t* nbr;
+  const float* scale; const float* shift; const float* residual;
+  int relu;
+  float* out;
+  int64_t n_out;
+};
+
 // ---- packed coordinate keys: [ batch:10 | x:18 | y:18 | z:18 ], biased by 2^17 ---------------------------
 constexpr int kAxisBits = 18;
 constexpr int kAxisBias = 1 << 17;

@@ -10,18 +10,6 @@
 
 namespace gclb {
 
-struct ConvParams {
-  const float* in0; const float* in1;
-  int c0, c1;
-  const float* W;
-  int K, cout;
-  const int32_t* nbr;
-  const float* scale; const float* shift; const float* residual;
-  int relu;
-  float* out;
-  int64_t n_out;
-};
-
 constexpr int BK = 32;
 constexpr int kConvThreads = 256;
 
@@ -347,9 +335,9 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
   ConvParams p{in0, in1, c0, c1, W, K, cout, nbr, scale, shift, residual, relu, out, n_out};
   const int cin = c0 + c1;
   cudaError_t e;
-  if (algo != 1 && spconv_tc_supported(p)) return spconv_fwd_tc(p, n_in, st);
-  if (algo == 2) {
-    set_error("gclb_spconv_fwd: shape (cin=%d, cout=%d, K=%d) is not covered by the tcgen05 kernel", cin, cout, K);
+  if (algo == 2) {   // W is in the tensor-core layout [K][cout][cin]
+    if (spconv_tc_supported(p)) return spconv_fwd_tc(p, n_in, st);
+    set_error("gclb_spconv_fwd: shape (c0=%d, c1=%d, cout=%d, K=%d) is not covered by the tcgen05 kernel", c0, c1, cout, K);
     return GCLB_ERR_UNSUPPORTED;
   }
   if (c1 == 0 && cin <= 4 && (size_t)K * cin * cout * 4 <= 96 * 1024) {

@@ -42,15 +42,32 @@ class ResUNetEngine:
     for l in (2, 3, 4):
       self.p[f"conv{l}"] = f(getattr(model, f"conv{l}"), getattr(model, f"norm{l}"))
       self.p[f"conv{l}_tr"] = f(getattr(model, f"conv{l}_tr"), getattr(model, f"norm{l}_tr"))
+    T = type(model).TR_CHANNELS
+    self.SPLIT = {"conv3_tr": T[4], "conv2_tr": T[3]}
     self.W1 = model.conv1_tr.kernel.detach().to(d).float().contiguous()
     self.W2 = model.final.kernel.detach().to(d).float().contiguous()
     self.bias = model.final.bias.detach().to(d).float().reshape(-1).contiguous() if model.final.bias is not None else None
     self.last_maps = None
 
+    # tensor-core weight copies ([K, Cout, Cin], tf32-rounded) for every layer the tcgen05 kernel covers
+    self.tc = {}
+    if algo != 1:
+      for key, (W, _, _) in self.p.items():
+        K, cin, cout = W.shape
+        c0 = self.SPLIT.get(key, cin)
+        if ops.tc_supported(c0, cin - c0, cout, K):
+          self.tc[key] = ops.weights_to_tc(W)
+
+  # first-source channel count of the layers that read a concatenation (ME.cat fused into the gather)
+  SPLIT = {}
+
   # ---- building blocks
   def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False):
     W, sc, sh = self.p[key]
-    return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=self.algo)
+    if key in self.tc:
+      return ops.spconv_fwd(x, self.tc[key], nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
+                            algo=2)
+    return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)
 
   def _block(self, name, x, nbr):
     n = x.shape[0]

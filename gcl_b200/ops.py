@@ -163,11 +163,15 @@ def kernel_map_pairs(nbr: torch.Tensor):
 def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
                out: Optional[torch.Tensor] = None, algo: int = 0) -> torch.Tensor:
-  """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path)."""
+  """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path); with algo=2 (tcgen05) W is the
+  tensor-core layout [K, Cout, Cin] from `weights_to_tc`."""
   require_cuda(in0, W, nbr, in1, scale, shift, residual)
   if W.dim() == 2:
     W = W.unsqueeze(0)
-  K, cin, cout = W.shape
+  if algo == 2:
+    K, cout, cin = W.shape
+  else:
+    K, cin, cout = W.shape
   c0 = in0.shape[1]
   c1 = in1.shape[1] if in1 is not None else 0
   assert c0 + c1 == cin, f"channel mismatch: {c0}+{c1} vs {cin}"
@@ -179,6 +183,21 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
        ptr(scale), ptr(shift), ptr(residual), int(bool(relu)), ptr(out), n_out, algo, stream())
   return out
+
+
+def weights_to_tc(W: torch.Tensor) -> torch.Tensor:
+  """[K, Cin, Cout] (or [Cin, Cout]) -> tensor-core layout [K, Cout, Cin], rounded to tf32 (once per layer)."""
+  require_cuda(W)
+  W3 = (W if W.dim() == 3 else W.unsqueeze(0)).contiguous().float()
+  K, cin, cout = W3.shape
+  Wt = torch.empty((K, cout, cin), dtype=torch.float32, device=W.device)
+  call("gclb_weights_to_tc", ptr(W3), K, cin, cout, ptr(Wt), stream())
+  return Wt
+
+
+def tc_supported(c0: int, c1: int, cout: int, K: int) -> bool:
+  return (_lib.load().gclb_has_tcgen05() == 1 and c0 % 32 == 0 and c1 % 32 == 0 and c0 >= 32
+          and cout in (32, 64, 128, 256) and K <= 27)
 
 
 def spconv_wgrad(x: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int) -> torch.Tensor:

@@ -118,8 +118,13 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
  *   nbr int32 [n_out, K] or NULL (K==1: identity map, the kernel_size==1 `F.mm` path)
  *   scale, shift float32 [cout] or NULL    : folded eval-mode BatchNorm / bias
  *   residual float32 [n_out, cout] or NULL ; relu 0/1
- *   algo: 0 = auto, 1 = fp32 CUDA-core kernel (exact fp32), 2 = tcgen05 kind::tf32 (fp32 accumulate in TMEM)
+ *   algo: 0/1 = fp32 CUDA-core kernel (exact fp32; any channel counts);
+ *         2   = tcgen05 kind::tf32 tensor-core kernel, fp32 accumulate in TMEM.  W must then be in the tensor-core
+ *               layout [K, cout, c0+c1] produced by gclb_weights_to_tc; needs c0 % 32 == 0, c1 % 32 == 0,
+ *               cout in {32, 64, 128, 256}, K <= 27 (otherwise GCLB_ERR_UNSUPPORTED).
  * ---------------------------------------------------------------------------------------------------- */
+/* W [K, cin, cout] (ME layout) -> Wt [K, cout, cin], values rounded to nearest tf32 (done once per layer) */
+int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream);
 int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
                     int32_t K, int32_t cout, const int32_t* nbr, const float* scale, const float* shift,
                     const float* residual, int32_t relu, float* out, int64_t n_out, int32_t algo, void* stream);

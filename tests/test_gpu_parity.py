@@ -168,14 +168,45 @@ def test_spconv_fwd_vs_oracle(G, cin, cout, ks):
   nbr_d = torch.from_numpy(nbr).int().to(G.dev)
   got = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, algo=1)
   assert _rel(got, ref) < FP32_TOL
-  got = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, algo=0)
-  assert _rel(got, ref) < FEAT_TOL
+  if G.ops.tc_supported(cin, 0, cout, ks ** 3):   # tcgen05 kind::tf32 path, tensor-core weight layout
+    Wt = G.ops.weights_to_tc(W.to(G.dev))
+    got = G.ops.spconv_fwd(x.to(G.dev), Wt, nbr_d, n, algo=2)
+    assert _rel(got, ref) < FEAT_TOL
+    assert (got.cpu() - ref).abs().max() < 5e-3 * ref.abs().max()
   # fused epilogue: scale/shift, residual, relu
   sc, sh, res = torch.rand(cout) + 0.5, torch.randn(cout), torch.randn(n, cout)
   ref2 = torch.relu(ref * sc + sh + res)
   got2 = G.ops.spconv_fwd(x.to(G.dev), W.to(G.dev), nbr_d, n, scale=sc.to(G.dev), shift=sh.to(G.dev),
                           residual=res.to(G.dev), relu=True, algo=1)
   assert _rel(got2, ref2) < FP32_TOL
+
+
+@pytest.mark.parametrize("n,cin,cout", [(128, 32, 32), (1000, 64, 64), (5000, 96, 64), (333, 256, 256), (77, 128, 128)])
+def test_tc_dense_pointwise_gemm(G, n, cin, cout):
+  """K == 1 (identity map) through the tcgen05 kernel is a dense GEMM: pins descriptors / swizzle / TMEM readout."""
+  torch.manual_seed(n)
+  x, W = torch.randn(n, cin), torch.randn(1, cin, cout) / np.sqrt(cin)
+  ref = x @ W[0]
+  got = G.ops.spconv_fwd(x.to(G.dev), G.ops.weights_to_tc(W.to(G.dev)), None, n, algo=2)
+  assert _rel(got, ref) < FEAT_TOL
+  # exact when the inputs are tf32-representable (integers): proves the only error source is operand rounding
+  xi, Wi = torch.randint(-4, 5, (n, cin)).float(), torch.randint(-4, 5, (1, cin, cout)).float()
+  got = G.ops.spconv_fwd(xi.to(G.dev), G.ops.weights_to_tc(Wi.to(G.dev)), None, n, algo=2)
+  assert torch.equal(got.cpu(), xi @ Wi[0])
+
+
+def test_tc_two_source_epilogue(G):
+  torch.manual_seed(6)
+  C_ref, _ = _oracle_voxelize([_random_cloud(23, 5000, 9.0)], 0.3)
+  n = len(C_ref)
+  nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(3, 1))
+  a, b = torch.randn(n, 64), torch.randn(n, 64)
+  W = torch.randn(27, 128, 64) / 60
+  sc, sh, res = torch.rand(64) + 0.5, torch.randn(64), torch.randn(n, 64)
+  ref = torch.relu(OME.sparse_conv_reference(torch.cat([a, b], 1), W, nbr, n) * sc + sh + res)
+  got = G.ops.spconv_fwd(a.to(G.dev), G.ops.weights_to_tc(W.to(G.dev)), torch.from_numpy(nbr).int().to(G.dev), n,
+                         in1=b.to(G.dev), scale=sc.to(G.dev), shift=sh.to(G.dev), residual=res.to(G.dev), relu=True, algo=2)
+  assert _rel(got, ref) < FEAT_TOL
 
 
 def test_spconv_two_source_and_pointwise(G):
