@@ -1,0 +1,57 @@
+"""CPU: the oracle against the committed golden vectors, which were produced by the REFERENCE's own Python
+(tests/golden/make_golden.py: model/resunet.py, lib/eval.py, lib/colocation_trainer.py imported in the build container)."""
+import os
+
+import numpy as np
+import torch
+
+import oracle.me_cpu as OME
+from oracle import gcl_loss as oloss
+from oracle import matching as omatch
+from gcl_b200.resunet import make_models
+from helpers import numpy_seeded_weights
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_resunet_restatement_matches_reference_model_output():
+  g = np.load(os.path.join(GOLD, "resunet_bn2c.npz"))
+  C = torch.from_numpy(g["coords"])
+  model = make_models(OME)["ResUNetBN2C"](1, 32, bn_momentum=0.05, conv1_kernel_size=5, normalize_feature=True)
+  numpy_seeded_weights(model, seed=int(g["weight_seed"])).eval()
+  with torch.no_grad():
+    out = model(OME.SparseTensor(torch.ones(len(C), 1), coordinates=C)).F
+  ref = torch.from_numpy(g["feats_out"])
+  assert out.shape == ref.shape
+  assert (out - ref).abs().max() < 2e-5          # same graph, same operators; only BLAS summation order may differ
+
+
+def test_nn_matches_reference_find_nn_gpu():
+  g = np.load(os.path.join(GOLD, "nn.npz"))
+  F0, F1 = torch.from_numpy(g["F0"]), torch.from_numpy(g["F1"])
+  idx, d = omatch.find_nn(F0, F1, nn_max_n=250, return_distance=True)
+  assert np.array_equal(idx.numpy(), g["idx"]) and np.allclose(d.numpy(), g["dist"], atol=1e-7)
+  idx2, d2 = omatch.find_nn(F0, F1, return_distance=True, dist_type="L2")
+  assert np.array_equal(idx2.numpy(), g["idx_l2"]) and np.allclose(d2.numpy(), g["dist_l2"], atol=1e-6)
+  pairs, _, _ = omatch.mutual_nn(F0, F1)
+  assert np.array_equal(pairs, g["mutual_pairs"])
+
+
+def test_gcl_loss_matches_reference_trainer():
+  g = np.load(os.path.join(GOLD, "gcl_loss.npz"))
+  for name, square, finest in (("finest_sq", True, True), ("finest_l2", False, True), ("location", False, False)):
+    F = torch.from_numpy(g["F"]).clone().requires_grad_(True)
+    np.random.seed(5)
+    sel = oloss.draw_selections(len(g["group"]), len(F), 256, 512)
+    pos, fin, neg = oloss.group_contrastive_loss(F, g["group"], g["index"], g["index_hash"], g["finest_flag"], *sel,
+                                                 square_loss=square, with_finest=finest)
+    (1.0 * pos + 0.5 * fin + 2.0 * neg).backward()
+    want = g[name + "_losses"]
+    assert np.allclose([pos.item(), fin.item(), neg.item()], want, rtol=1e-5, atol=1e-7), name
+    assert torch.allclose(F.grad, torch.from_numpy(g[name + "_grad"]), atol=1e-7, rtol=1e-4), name
+
+
+def test_exhaustive_hash_symmetry():
+  h = oloss.exhaustive_hash([[3, 7, 9], [1, 2]], 100)
+  assert sorted(h.tolist()) == sorted([3 * 100 + 7, 3 * 100 + 9, 7 * 100 + 9, 1 * 100 + 2])
+  assert oloss.neg_hash([7], [3], 100)[0] == oloss.neg_hash([3], [7], 100)[0] == 307
