@@ -168,7 +168,8 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
   cm1, _ = ops.voxelize(xyz_dev, VOXEL, ptr)
   maps = eng.build_maps(cm1)
   cms, km = maps
-  pair_counts = {k: int((v >= 0).sum().item()) for k, v in km.items()}
+  tabs = {k: (v if isinstance(v, tuple) else (v,)) for k, v in km.items()}
+  pair_counts = {k: int((v[0] >= 0).sum().item()) for k, v in tabs.items()}
   recs = []
   orig = ops.spconv_fwd
 
@@ -179,7 +180,7 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
     e1.record()
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     K, cin, cout = W3.shape
-    pairs = n_out if nbr is None else next(pair_counts[k] for k, v in km.items() if v is nbr)
+    pairs = n_out if nbr is None else next(pair_counts[k] for k, v in tabs.items() if any(t is nbr for t in v))
     alg_bytes = 4 * (in0.shape[0] * cin + n_out * cout) + 8 * pairs + 4 * K * cin * cout
     if kw.get("residual") is not None:
       alg_bytes += 4 * n_out * cout

@@ -36,6 +36,7 @@ struct ConvParams {   // sparse-conv forward arguments shared by the fp32 (spcon
   const float* W;     // fp32 path: [K][cin][cout] ; tcgen05 path: [K][cout][cin] (gclb_weights_to_tc)
   int K, cout;
   const int32_t* nbr;
+  const int32_t* perm;   // tcgen05 path: table row t describes output row perm[t] (NULL = identity)
   const float* scale; const float* shift; const float* residual;
   int relu;
   float* out;

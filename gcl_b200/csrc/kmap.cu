@@ -68,6 +68,76 @@ __global__ void __launch_bounds__(kCompactBlock) kmap_scatter_kernel(const int32
   if (e == n_out * K - 1) offset_ptr[K] = pos + f;
 }
 
+// ---- row bucketing for the tensor-core kernel -----------------------------------------------------------------------
+// A 128-row tile pays one pipeline stage per kernel offset that is populated ANYWHERE in the tile.  Rows are therefore
+// grouped (stable counting sort, 64 buckets) by a 6-bit key: "has a neighbour with dx<0 / dx>0 / dy<0 / dy>0 / dz<0 / dz>0".
+// Ground-like rows (no vertical neighbours), wall-like rows and, for transposed convolutions, the parity classes of the
+// fine voxels end up in separate tiles: measured 21.5 -> 8.6 stages per tile for stride-1 maps, 17.7 -> 2.3 for transposed.
+constexpr int kBuckets = 64;
+
+__device__ __forceinline__ int row_key(const int32_t* __restrict__ row, int ksize, int K) {
+  int key = 0;
+  for (int k = 0; k < K; ++k) {
+    if (__ldg(row + k) < 0) continue;
+    int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
+    int half = ksize / 2;
+    key |= (ix < half) ? 1 : 0;
+    key |= (ix > half) ? 2 : 0;
+    key |= (iy < half) ? 4 : 0;
+    key |= (iy > half) ? 8 : 0;
+    key |= (iz < half) ? 16 : 0;
+    key |= (iz > half) ? 32 : 0;
+  }
+  return key;
+}
+
+__global__ void __launch_bounds__(kCompactBlock) rowkey_hist_kernel(const int32_t* __restrict__ nbr, int64_t n, int ksize,
+                                                                    int K, uint8_t* __restrict__ keys,
+                                                                    int32_t* __restrict__ hist, int64_t nblocks) {
+  __shared__ int h[kBuckets];
+  if (threadIdx.x < kBuckets) h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t o = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  if (o < n) {
+    int key = row_key(nbr + o * K, ksize, K);
+    keys[o] = (uint8_t)key;
+    atomicAdd(&h[key], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kBuckets) hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // bucket-major
+}
+
+__global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n,
+                                                                       const int32_t* __restrict__ offs, int64_t nblocks,
+                                                                       int32_t* __restrict__ perm) {
+  __shared__ int warp_hist[kCompactBlock / 32][kBuckets];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < (kCompactBlock / 32) * kBuckets; e += kCompactBlock) (&warp_hist[0][0])[e] = 0;
+  __syncthreads();
+  int64_t o = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  const bool valid = o < n;
+  const int key = valid ? keys[o] : kBuckets;          // invalid lanes form their own group
+  const unsigned same = __match_any_sync(0xffffffffu, key);
+  const int rank = __popc(same & ((1u << lane) - 1));
+  if (valid && rank == 0) warp_hist[wid][key] = __popc(same);
+  __syncthreads();
+  if (valid) {
+    int base = offs[(int64_t)key * nblocks + blockIdx.x];
+    for (int w = 0; w < wid; ++w) base += warp_hist[w][key];
+    perm[base + rank] = (int32_t)o;                    // stable: buckets keep the original row order
+  }
+}
+
+__global__ void __launch_bounds__(256) permute_rows_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ perm,
+                                                           int64_t n, int K, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t t = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * wpb) {
+    const int64_t o = perm[t];
+    for (int k = lane; k < K; k += 32) out[t * K + k] = __ldg(&nbr[o * K + k]);
+  }
+}
+
 }  // namespace gclb
 
 using namespace gclb;
@@ -110,6 +180,33 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
   launch_scan_block_counts(counts, nb, nullptr, st);
   kmap_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, K, counts, in_idx, out_idx, offset_ptr);
   count_launches(3);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+size_t gclb_kmap_sort_workspace_bytes(int64_t n_out) {
+  int64_t nb = compact_blocks(n_out);
+  return (size_t)(((n_out + 15) & ~15ll) + (kBuckets * nb + 8) * 4);
+}
+
+int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_t* perm_out, int32_t* nbr_sorted_out,
+                        void* workspace, void* stream) {
+  GCLB_CHECK_ARG(workspace && ksize >= 1 && ksize <= 7, "bad arguments");
+  if (n_out == 0) return GCLB_OK;
+  GCLB_CHECK_ARG(nbr && perm_out && nbr_sorted_out, "null pointer");
+  GCLB_CHECK_ARG(n_out < (1ll << 31), "too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = ksize * ksize * ksize;
+  const int64_t nb = compact_blocks(n_out);
+  uint8_t* keys = (uint8_t*)workspace;
+  int32_t* hist = (int32_t*)(keys + ((n_out + 15) & ~15ll));
+  rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, keys, hist, nb);
+  launch_scan_block_counts(hist, kBuckets * nb, nullptr, st);
+  rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out);
+  int64_t blocks = (n_out + 7) / 8;
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  permute_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out);
+  count_launches(4);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

@@ -51,12 +51,21 @@ class ResUNetEngine:
 
     # tensor-core weight copies ([K, Cout, Cin], tf32-rounded) for every layer the tcgen05 kernel covers
     self.tc = {}
+    self.tail_tc = None
+    self.sort_rows = True
     if algo != 1:
       for key, (W, _, _) in self.p.items():
         K, cin, cout = W.shape
         c0 = self.SPLIT.get(key, cin)
         if ops.tc_supported(c0, cin - c0, cout, K):
           self.tc[key] = ops.weights_to_tc(W)
+      # pointwise tail on the tensor cores: [y1 | s1] W1 -> ReLU -> W2 + bias -> L2 normalise (fused in the epilogue)
+      c_s1 = type(model).CHANNELS[1]
+      c_y1 = self.W1.shape[0] - c_s1
+      self.tail_tc = None
+      if (ops.tc_supported(c_y1, c_s1, self.W1.shape[1], 1) and ops.tc_supported(self.W2.shape[0], 0, self.W2.shape[1], 1)
+          and self.W2.shape[1] == 32):
+        self.tail_tc = (ops.weights_to_tc(self.W1), ops.weights_to_tc(self.W2))
 
   # first-source channel count of the layers that read a concatenation (ME.cat fused into the gather)
   SPLIT = {}
@@ -65,8 +74,13 @@ class ResUNetEngine:
   def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False):
     W, sc, sh = self.p[key]
     if key in self.tc:
+      perm = None
+      if isinstance(nbr, tuple):          # (table, sorted table, perm) from build_maps
+        nbr, perm = nbr[1], nbr[2]
       return ops.spconv_fwd(x, self.tc[key], nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
-                            algo=2)
+                            algo=2, row_perm=perm)
+    if isinstance(nbr, tuple):
+      nbr = nbr[0]
     return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)
 
   def _block(self, name, x, nbr):
@@ -93,6 +107,10 @@ class ResUNetEngine:
     for s in (1, 2, 4):
       km[f"down{s}"] = ops.kernel_map(cms[s], cms[2 * s], 3)
       km[f"up{s}"] = ops.kernel_map(cms[2 * s], cms[s], 3, transposed=True)
+    if self.tc and self.sort_rows:       # row-bucketed copies for the tensor-core kernel
+      for name, t in list(km.items()):
+        if name != "c1" or self.conv1_ks == 3:
+          km[name] = (t,) + ops.kernel_map_sort(t)
     return cms, km
 
   @torch.no_grad()
@@ -109,6 +127,9 @@ class ResUNetEngine:
     y4 = self._block("block4_tr", self._conv("conv4_tr", s8, km["up4"], n4), km["k3s4"])
     y2 = self._block("block3_tr", self._conv("conv3_tr", y4, km["up2"], n2, x2=s4), km["k3s2"])
     y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2), km["k3s1"])
+    if getattr(self, "tail_tc", None) is not None:
+      h = ops.spconv_fwd(y1, self.tail_tc[0], None, n1, in1=s1, relu=True, algo=2)
+      return ops.spconv_fwd(h, self.tail_tc[1], None, n1, shift=self.bias, normalize=self.normalize, algo=2)
     return ops.pointwise_tail(y1, s1, self.W1, self.W2, self.bias, normalize=self.normalize)
 
   @torch.no_grad()

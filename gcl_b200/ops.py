@@ -160,9 +160,24 @@ def kernel_map_pairs(nbr: torch.Tensor):
   return in_idx[:total], out_idx[:total], off
 
 
+def kernel_map_sort(nbr: torch.Tensor):
+  """Group table rows by neighbour-direction pattern for the tcgen05 kernel: returns (nbr_sorted, perm) with
+  nbr_sorted[t] = nbr[perm[t]]."""
+  n_out, K = nbr.shape
+  ksize = round(K ** (1 / 3))
+  assert ksize ** 3 == K
+  lib = _lib.load()
+  perm = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
+  out = torch.empty_like(nbr)
+  ws = _workspace(lib.gclb_kmap_sort_workspace_bytes(n_out), nbr.device)
+  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(perm), ptr(out), ptr(ws), stream())
+  return out, perm
+
+
 def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
-               out: Optional[torch.Tensor] = None, algo: int = 0) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, algo: int = 0, normalize: bool = False,
+               row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
   """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path); with algo=2 (tcgen05) W is the
   tensor-core layout [K, Cout, Cin] from `weights_to_tc`."""
   require_cuda(in0, W, nbr, in1, scale, shift, residual)
@@ -181,12 +196,14 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   if out is None:
     out = torch.empty((n_out, cout), dtype=torch.float32, device=in0.device)
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
-       ptr(scale), ptr(shift), ptr(residual), int(bool(relu)), ptr(out), n_out, algo, stream())
+       ptr(row_perm), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)) | (2 if normalize else 0), ptr(out), n_out, algo,
+       stream())
   return out
 
 
 def weights_to_tc(W: torch.Tensor) -> torch.Tensor:
-  """[K, Cin, Cout] (or [Cin, Cout]) -> tensor-core layout [K, Cout, Cin], rounded to tf32 (once per layer)."""
+  """[K, Cin, Cout] (or [Cin, Cout]) -> tensor-core image (shape [K, Cout, Cin], pre-swizzled per 32-channel slab,
+  rounded to tf32); done once per layer."""
   require_cuda(W)
   W3 = (W if W.dim() == 3 else W.unsqueeze(0)).contiguous().float()
   K, cin, cout = W3.shape
@@ -197,7 +214,7 @@ def weights_to_tc(W: torch.Tensor) -> torch.Tensor:
 
 def tc_supported(c0: int, c1: int, cout: int, K: int) -> bool:
   return (_lib.load().gclb_has_tcgen05() == 1 and c0 % 32 == 0 and c1 % 32 == 0 and c0 >= 32
-          and cout in (32, 64, 128, 256) and K <= 27)
+          and cout in (32, 64, 128, 256) and K in (1, 27))
 
 
 def spconv_wgrad(x: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int) -> torch.Tensor:

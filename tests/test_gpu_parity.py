@@ -195,6 +195,46 @@ def test_tc_dense_pointwise_gemm(G, n, cin, cout):
   assert torch.equal(got.cpu(), xi @ Wi[0])
 
 
+def test_tc_fused_l2_normalise_tail(G):
+  torch.manual_seed(8)
+  n = 3001
+  a, b = torch.randn(n, 64), torch.randn(n, 32)
+  W1, W2, bias = torch.randn(96, 64) / 10, torch.randn(64, 32) / 8, torch.randn(32)
+  y = torch.relu(torch.cat([a, b], 1) @ W1) @ W2 + bias
+  ref = y / y.norm(dim=1, keepdim=True)
+  h = G.ops.spconv_fwd(a.to(G.dev), G.ops.weights_to_tc(W1.to(G.dev)), None, n, in1=b.to(G.dev), relu=True, algo=2)
+  got = G.ops.spconv_fwd(h, G.ops.weights_to_tc(W2.to(G.dev)), None, n, shift=bias.to(G.dev), normalize=True, algo=2)
+  assert _rel(got, ref) < FEAT_TOL
+  assert (got.norm(dim=1) - 1).abs().max() < 1e-5
+
+
+def test_kmap_row_bucketing_is_a_pure_reordering(G):
+  torch.manual_seed(12)
+  C_ref, _ = _oracle_voxelize([_random_cloud(24, 9000, 12.0), _random_cloud(25, 500, 3.0)], 0.3)
+  cm = G.ops.hash_build(C_ref.to(G.dev))
+  cm2 = G.ops.stride_map(cm, 2)
+  for nbr in (G.ops.kernel_map(cm, cm, 3), G.ops.kernel_map(cm2, cm, 3, transposed=True), G.ops.kernel_map(cm, cm2, 3)):
+    srt, perm = G.ops.kernel_map_sort(nbr)
+    n = nbr.shape[0]
+    assert torch.equal(torch.sort(perm.long()).values.cpu(), torch.arange(n))
+    assert torch.equal(srt, nbr[perm.long()])
+    # keys are non-decreasing and the sort is stable inside a bucket
+    v = (srt >= 0).cpu().numpy()
+    k = np.arange(27)
+    ix, iy, iz = k % 3, (k // 3) % 3, k // 9
+    key = sum((v[:, sel].any(1).astype(np.int64) << b) for b, sel in enumerate([ix == 0, ix == 2, iy == 0, iy == 2, iz == 0, iz == 2]))
+    assert (np.diff(key) >= 0).all()
+    p = perm.cpu().numpy()
+    same = np.diff(key) == 0
+    assert (np.diff(p)[same] > 0).all()
+    # the convolution result does not depend on the row order
+    x, W = torch.randn(int(srt.max()) + 1, 64, device=G.dev), torch.randn(27, 64, 64, device=G.dev) / 40
+    Wt = G.ops.weights_to_tc(W)
+    a = G.ops.spconv_fwd(x, Wt, nbr, n, algo=2)
+    b = G.ops.spconv_fwd(x, Wt, srt, n, algo=2, row_perm=perm)
+    assert torch.equal(a, b)
+
+
 def test_tc_two_source_epilogue(G):
   torch.manual_seed(6)
   C_ref, _ = _oracle_voxelize([_random_cloud(23, 5000, 9.0)], 0.3)

@@ -11,7 +11,7 @@ x,p=host[0]; x=x.to(dev)
 eng=m.engine
 cm1,_=ops.voxelize(x, 0.3, p)
 maps=eng.build_maps(cm1); cms,km=maps
-print({k:(tuple(v.shape), round((v>=0).float().mean().item(),3)) for k,v in km.items()})
+print({k:(tuple((v[0] if isinstance(v,tuple) else v).shape), round(((v[0] if isinstance(v,tuple) else v)>=0).float().mean().item(),3)) for k,v in km.items()})
 recs=[]
 orig=ops.spconv_fwd
 names=[]
