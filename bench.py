@@ -291,7 +291,7 @@ def main():
   def step_resident(s):
     x, p = resident[s % n_batches]
     out = matcher.match(x, p)
-    return sum(out["n_voxels"])
+    return out["n_voxels_total"]
 
   d2h_bytes = [0]
 
@@ -302,7 +302,7 @@ def main():
     k = int(pp[-1])
     pairs = out["pairs"][:k].cpu()
     d2h_bytes[0] = pairs.numel() * 8 + pp.numel() * 8
-    return sum(out["n_voxels"])
+    return out["n_voxels_total"]
 
   for s in range(args.warmup):
     step_resident(s)

@@ -25,7 +25,7 @@ SIGNATURES = {
     "gclb_compact_workspace_bytes": (_sz, [_i64]),
     "gclb_voxelize": (C.c_int, [_p, _i64, _p, _i32, _f32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_quantize_rows": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
-    "gclb_stride_map": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p]),
+    "gclb_stride_map": (C.c_int, [_p, _i64, _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "gclb_kmap_build": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "gclb_kmap_pairs": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "gclb_kmap_sort_workspace_bytes": (_sz, [_i64]),
@@ -38,7 +38,8 @@ SIGNATURES = {
     "gclb_affine_act": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "gclb_bn_stats": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "gclb_nn_workspace_bytes": (_sz, [_i64, _i64]),
-    "gclb_nn": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p]),
+    "gclb_nn": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p]),
+    "gclb_subsample": (C.c_int, [_p, _p, _i64, _i32, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),
     "gclb_mutual_filter": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p]),
     "gclb_loss_workspace_bytes": (_sz, [_i64, _i64]),
     "gclb_group_loss": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _f32, _f32, _f32,

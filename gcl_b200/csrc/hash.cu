@@ -71,9 +71,10 @@ struct StrideSource {  // parent coordinate map rows floored to a coarser lattic
 };
 
 template <class Src>
-__global__ void __launch_bounds__(256) insert_rows_kernel(Src src, int64_t n, HashTable t, int32_t* slot_of,
-                                                          int32_t* status) {
+__global__ void __launch_bounds__(256) insert_rows_kernel(Src src, int64_t n, const int64_t* n_dev, HashTable t,
+                                                          int32_t* slot_of, int32_t* status) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   if (i >= n) return;
   int b, x, y, z;
   bool ok = src.get(i, b, x, y, z) && coord_in_range(b, x, y, z);
@@ -92,9 +93,10 @@ __device__ __forceinline__ bool is_winner(const HashTable& t, const int32_t* slo
   return s >= 0 && t.vals[s] == (int)i;
 }
 
-__global__ void __launch_bounds__(kCompactBlock) count_winners_kernel(int64_t n, HashTable t, const int32_t* slot_of,
-                                                                      int32_t* counts) {
+__global__ void __launch_bounds__(kCompactBlock) count_winners_kernel(int64_t n, const int64_t* n_dev, HashTable t,
+                                                                      const int32_t* slot_of, int32_t* counts) {
   int64_t i = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   int f = (i < n) && is_winner(t, slot_of, i);
   int c = __syncthreads_count(f);
   if (threadIdx.x == 0) counts[blockIdx.x] = c;
@@ -126,11 +128,13 @@ void launch_scan_block_counts(int32_t* counts, int64_t nblocks, int64_t* total_o
 }
 
 template <class Src>
-__global__ void __launch_bounds__(kCompactBlock) scatter_winners_kernel(Src src, int64_t n, HashTable t,
-                                                                        const int32_t* slot_of, const int32_t* counts,
-                                                                        int32_t* coords4_out, int64_t* unique_map_out) {
+__global__ void __launch_bounds__(kCompactBlock) scatter_winners_kernel(Src src, int64_t n, const int64_t* n_dev,
+                                                                        HashTable t, const int32_t* slot_of,
+                                                                        const int32_t* counts, int32_t* coords4_out,
+                                                                        int64_t* unique_map_out) {
   __shared__ int total;
   int64_t i = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   int f = (i < n) && is_winner(t, slot_of, i);
   int pos = counts[blockIdx.x] + block_exclusive_scan(f, &total);
   if (f) {
@@ -144,16 +148,17 @@ __global__ void __launch_bounds__(kCompactBlock) scatter_winners_kernel(Src src,
   }
 }
 
-__global__ void __launch_bounds__(256) inverse_map_kernel(int64_t n, HashTable t, const int32_t* slot_of,
-                                                          int32_t* inverse) {
+__global__ void __launch_bounds__(256) inverse_map_kernel(int64_t n, const int64_t* n_dev, HashTable t,
+                                                          const int32_t* slot_of, int32_t* inverse) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   if (i >= n) return;
   int s = slot_of[i];
   inverse[i] = s >= 0 ? t.vals[s] : -1;
 }
 
 template <class Src>
-static int dedupe_rows(Src src, int64_t n, void* table, int64_t capacity, int32_t* coords4_out,
+static int dedupe_rows(Src src, int64_t n, const int64_t* n_dev, void* table, int64_t capacity, int32_t* coords4_out,
                        int64_t* unique_map_out, int32_t* inverse_out, int64_t* n_out, int32_t* status,
                        void* workspace, cudaStream_t st) {
   if (capacity < 2 || (capacity & (capacity - 1)) != 0 || capacity < n) {
@@ -171,12 +176,12 @@ static int dedupe_rows(Src src, int64_t n, void* table, int64_t capacity, int32_
   int32_t* slot_of = (int32_t*)workspace;
   int32_t* counts = slot_of + ((n + 3) & ~3ll);
   int64_t nb = compact_blocks(n);
-  insert_rows_kernel<Src><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, n, t, slot_of, status);
-  count_winners_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(n, t, slot_of, counts);
+  insert_rows_kernel<Src><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, n, n_dev, t, slot_of, status);
+  count_winners_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(n, n_dev, t, slot_of, counts);
   scan_block_counts_kernel<<<1, 1024, 0, st>>>(counts, nb, n_out);
-  scatter_winners_kernel<Src><<<(unsigned)nb, kCompactBlock, 0, st>>>(src, n, t, slot_of, counts, coords4_out,
+  scatter_winners_kernel<Src><<<(unsigned)nb, kCompactBlock, 0, st>>>(src, n, n_dev, t, slot_of, counts, coords4_out,
                                                                       unique_map_out);
-  if (inverse_out) inverse_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, t, slot_of, inverse_out);
+  if (inverse_out) inverse_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, n_dev, t, slot_of, inverse_out);
   count_launches(inverse_out ? 5 : 4);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
@@ -262,8 +267,8 @@ int gclb_voxelize(const float* xyz, int64_t P, const int64_t* cloud_ptr, int32_t
   GCLB_CHECK_ARG(voxel > 0.f && n_clouds >= 1 && n_clouds < 1023, "bad voxel size or cloud count");
   GCLB_CHECK_ARG(P < (1ll << 31), "too many points for int32 row indices");
   XyzSource src{xyz, cloud_ptr, n_clouds, voxel};
-  return dedupe_rows(src, P, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status, workspace,
-                     (cudaStream_t)stream);
+  return dedupe_rows(src, P, nullptr, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status,
+                     workspace, (cudaStream_t)stream);
 }
 
 int gclb_quantize_rows(const int32_t* rows, int64_t P, int32_t width, void* table, int64_t capacity,
@@ -274,18 +279,18 @@ int gclb_quantize_rows(const int32_t* rows, int64_t P, int32_t width, void* tabl
   GCLB_CHECK_ARG(width == 3 || width == 4, "width must be 3 or 4");
   GCLB_CHECK_ARG(P < (1ll << 31), "too many rows for int32 row indices");
   RowsSource src{rows, width};
-  return dedupe_rows(src, P, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status, workspace,
+  return dedupe_rows(src, P, nullptr, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status, workspace,
                      (cudaStream_t)stream);
 }
 
-int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, int32_t new_stride, void* out_table, int64_t out_capacity,
-                    int32_t* out_coords4, int32_t* parent_row_out, int64_t* n_out, int32_t* status, void* workspace,
-                    void* stream) {
+int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in_dev, int32_t new_stride,
+                    void* out_table, int64_t out_capacity, int32_t* out_coords4, int32_t* parent_row_out, int64_t* n_out,
+                    int32_t* status, void* workspace, void* stream) {
   GCLB_CHECK_ARG(out_table && n_out && status && workspace, "null pointer");
   GCLB_CHECK_ARG(n_in == 0 || (in_coords4 && out_coords4), "null pointer");
   GCLB_CHECK_ARG(new_stride >= 1, "stride must be >= 1");
   StrideSource src{in_coords4, new_stride};
-  return dedupe_rows(src, n_in, out_table, out_capacity, out_coords4, nullptr, parent_row_out, n_out, status,
+  return dedupe_rows(src, n_in, n_in_dev, out_table, out_capacity, out_coords4, nullptr, parent_row_out, n_out, status,
                      workspace, (cudaStream_t)stream);
 }
 

@@ -21,16 +21,17 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 
 template <bool VEC>
-__device__ __forceinline__ void load_tile_T(float* S, const float* __restrict__ X, int64_t row0, int64_t nrows, int C,
-                                            int cs, int tid) {
-  // S[c][r] <- X[row0 + r][cs + c], 128 rows x 32 channels, zero filled outside
+__device__ __forceinline__ void load_tile_T(float* S, const float* __restrict__ X, const int64_t* __restrict__ rows,
+                                            int64_t row0, int64_t nrows, int C, int cs, int tid) {
+  // S[c][r] <- X[row(row0 + r)][cs + c], 128 rows x 32 channels, zero filled outside; row(i) = rows ? rows[i] : i
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     int e = pass * 256 + tid;
     int r = e / 8, cv = (e % 8) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nrows) {
-      const float* src = X + (size_t)(row0 + r) * C + cs + cv;
+      const int64_t gr = rows ? __ldg(rows + row0 + r) : row0 + r;
+      const float* src = X + (size_t)gr * C + cs + cv;
       if (VEC) {
         if (cs + cv < C) v = __ldg(reinterpret_cast<const float4*>(src));
       } else {
@@ -51,6 +52,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) nn_tile_kernel(const float* __restrict__ A, const float* __restrict__ B, int C,
                                                       const int64_t* __restrict__ a_ptr,
                                                       const int64_t* __restrict__ b_ptr,
+                                                      const int64_t* __restrict__ a_rows,
+                                                      const int64_t* __restrict__ b_rows,
                                                       unsigned long long* __restrict__ rowbest,
                                                       unsigned long long* __restrict__ colbest) {
   __shared__ __align__(16) float smem[2 * 32 * NPAD];
@@ -71,8 +74,8 @@ __global__ void __launch_bounds__(256) nn_tile_kernel(const float* __restrict__ 
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   for (int cs = 0; cs < C; cs += 32) {
-    load_tile_T<VEC>(As, A, a0 + tr, nrows, C, cs, tid);
-    load_tile_T<VEC>(Bs, B, b0 + tc, ncols, C, cs, tid);
+    load_tile_T<VEC>(As, A, a_rows, a0 + tr, nrows, C, cs, tid);
+    load_tile_T<VEC>(Bs, B, b_rows, b0 + tc, ncols, C, cs, tid);
     __syncthreads();
     const int kmax = min(32, C - cs);
 #pragma unroll 4
@@ -209,6 +212,80 @@ __global__ void __launch_bounds__(kCompactBlock) mutual_scatter_kernel(const int
   }
 }
 
+// ---- per-cloud random subsample without replacement (scripts/test_kitti.py:29-43 `np.random.choice(N, 5000, False)`) ----
+// rows of a batched coordinate map are grouped by cloud in order: cloud c owns rows [lower_bound(batch >= c), ...).
+__global__ void cloud_ranges_kernel(const int32_t* __restrict__ coords4, const int64_t* __restrict__ n_rows_dev,
+                                    int64_t n_rows, int n_clouds, int64_t S, int groups,
+                                    int64_t* __restrict__ cloud_ptr, int64_t* __restrict__ sel_ptr) {
+  __shared__ int64_t start[1025];
+  const int64_t n = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
+  for (int c = threadIdx.x; c <= n_clouds; c += blockDim.x) {
+    int64_t lo = 0, hi = n;                       // first row with batch >= c
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (__ldg(&coords4[4 * mid]) < c) lo = mid + 1; else hi = mid;
+    }
+    start[c] = lo;
+    cloud_ptr[c] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {   // group g = clouds g, g+groups, ...: its own CSR over the selected rows
+    const int g = threadIdx.x, n_seg = n_clouds / groups;
+    int64_t* sp = sel_ptr + (int64_t)g * (n_seg + 1);
+    int64_t acc = 0;
+    sp[0] = 0;
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+      int c = sgm * groups + g;
+      int64_t v = start[c + 1] - start[c];
+      acc += (S > 0 && v > S) ? S : v;
+      sp[sgm + 1] = acc;
+    }
+  }
+}
+
+// bijective mixer on `bits` bits (xorshift / odd multiply / add rounds), cycle-walked into [0, v): a pseudo-random
+// permutation of the cloud's rows; its first S images are a uniform-looking sample without replacement.
+__device__ __forceinline__ uint32_t mix_bits(uint32_t x, int bits, uint32_t k0, uint32_t k1) {
+  const uint32_t mask = (bits >= 32) ? 0xffffffffu : ((1u << bits) - 1u);
+  const int sh = max(1, bits / 2);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    x = (x + k0) & mask;
+    x = (x * 0x9E3779B1u) & mask;
+    x ^= x >> sh;
+    x = (x * (k1 | 1u)) & mask;
+    x ^= x >> sh;
+    k0 = k0 * 0x85EBCA6Bu + 0xC2B2AE35u;
+    k1 = k1 * 0x27D4EB2Fu + 0x165667B1u;
+  }
+  return x & mask;
+}
+
+__global__ void __launch_bounds__(256) subsample_kernel(const int64_t* __restrict__ cloud_ptr,
+                                                        const int64_t* __restrict__ sel_ptr_all, int n_clouds, int64_t S,
+                                                        int groups, int64_t group_capacity, uint64_t seed,
+                                                        int64_t* __restrict__ sel_all) {
+  const int c = blockIdx.y;
+  const int g = c % groups, sgm = c / groups, n_seg = n_clouds / groups;
+  const int64_t* sel_ptr = sel_ptr_all + (int64_t)g * (n_seg + 1) + sgm;
+  int64_t* sel = sel_all + (int64_t)g * group_capacity;
+  const int64_t begin = cloud_ptr[c], v = cloud_ptr[c + 1] - begin;
+  const int64_t m = sel_ptr[1] - sel_ptr[0];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int64_t pick = i;
+  if (m < v) {
+    int bits = 1;
+    while ((1ll << bits) < v) ++bits;
+    uint32_t k0 = (uint32_t)(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(c + 1)));
+    uint32_t k1 = (uint32_t)((seed >> 32) + 0x7F4A7C15u * (uint32_t)(c + 1));
+    uint32_t x = (uint32_t)i;
+    do { x = mix_bits(x, bits, k0, k1); } while ((int64_t)x >= v);
+    pick = (int64_t)x;
+  }
+  sel[sel_ptr[0] + i] = begin + pick;
+}
+
 int nn_tc(const float* A, const float* B, int C, const int64_t* a_ptr, const int64_t* b_ptr, int n_pairs,
           int64_t max_n, int64_t max_m, unsigned long long* rowbest, unsigned long long* colbest, cudaStream_t st);
 bool nn_tc_supported(int C);
@@ -226,8 +303,9 @@ size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total) {
 }
 
 int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, const int64_t* b_ptr, int32_t n_pairs,
-            int64_t n_total, int64_t m_total, int64_t max_n, int64_t max_m, int64_t* idx01, float* d01,
-            int64_t* idx10, float* d10, int32_t algo, void* workspace, void* stream) {
+            const int64_t* a_rows, const int64_t* b_rows, int64_t n_total, int64_t m_total, int64_t max_n,
+            int64_t max_m, int64_t* idx01, float* d01, int64_t* idx10, float* d10, int32_t algo, void* workspace,
+            void* stream) {
   GCLB_CHECK_ARG(a_ptr && b_ptr && workspace && n_pairs >= 1 && C >= 1, "bad arguments");
   GCLB_CHECK_ARG(n_total == 0 || (A && idx01), "null pointer");
   GCLB_CHECK_ARG(max_n <= n_total && max_m <= m_total, "max_n / max_m exceed totals");
@@ -249,8 +327,8 @@ int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, con
     } else {
       dim3 grid((unsigned)((max_m + NT - 1) / NT), (unsigned)((max_n + NT - 1) / NT), (unsigned)n_pairs);
       GCLB_CHECK_ARG(grid.y <= 65535, "too many row tiles");
-      if (C % 4 == 0) nn_tile_kernel<true><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, rowbest, colbest);
-      else nn_tile_kernel<false><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, rowbest, colbest);
+      if (C % 4 == 0) nn_tile_kernel<true><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
+      else nn_tile_kernel<false><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
       count_launches(1);
     }
   }
@@ -258,6 +336,25 @@ int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, con
   if (n_total > 0) nn_unpack_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(rowbest, n_total, idx01, d01);
   if (idx10 && m_total > 0)
     nn_unpack_kernel<<<(unsigned)((m_total + 255) / 256), 256, 0, st>>>(colbest, m_total, idx10, d10);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_subsample(const int32_t* coords4, const int64_t* n_rows_dev, int64_t n_rows, int32_t n_clouds, int64_t S,
+                   int32_t groups, uint64_t seed, int64_t* cloud_ptr_out, int64_t* sel_ptr_out, int64_t* sel_out,
+                   void* stream) {
+  GCLB_CHECK_ARG(cloud_ptr_out && sel_ptr_out && n_clouds >= 1 && n_clouds <= 1024, "bad arguments");
+  GCLB_CHECK_ARG(groups >= 1 && groups <= 8 && n_clouds % groups == 0, "n_clouds must be a multiple of groups");
+  GCLB_CHECK_ARG(n_rows == 0 || (coords4 && sel_out), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cloud_ranges_kernel<<<1, 256, 0, st>>>(coords4, n_rows_dev, n_rows, n_clouds, S, groups, cloud_ptr_out, sel_ptr_out);
+  int64_t per_cloud = (S > 0 && S < n_rows) ? S : n_rows;
+  if (per_cloud > 0) {
+    dim3 grid((unsigned)((per_cloud + 255) / 256), (unsigned)n_clouds);
+    subsample_kernel<<<grid, 256, 0, st>>>(cloud_ptr_out, sel_ptr_out, n_clouds, S, groups,
+                                           per_cloud * (n_clouds / groups), seed, sel_out);
+  }
+  count_launches(2);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

@@ -89,15 +89,13 @@ class ResUNetEngine:
     return self._conv(name + ".2", t, nbr, n, residual=x, relu=True)
 
   def build_maps(self, cm1: ops.CoordMap):
-    """strided maps + all kernel maps of one forward (cached by the caller for repeated forwards)."""
+    """strided maps + all kernel maps of one forward (cacheable by the caller for repeated forwards).  The three
+    strided levels are chained on the device and finished -- together with cm1 if it came from voxelize(sync=False) --
+    by ONE host read of the row counts."""
     cm2 = ops.stride_map(cm1, 2, sync=False)
-    # the child maps need their parent's row count on the host for launch sizing: one sync per level would
-    # serialise, so build each level from the (worst-case sized) parent and read all counts at once
-    ops.finish_stride_maps([cm2])
     cm4 = ops.stride_map(cm2, 2, sync=False)
-    ops.finish_stride_maps([cm4])
     cm8 = ops.stride_map(cm4, 2, sync=False)
-    ops.finish_stride_maps([cm8])
+    ops.finish_maps([cm1, cm2, cm4, cm8])
     cms = {1: cm1, 2: cm2, 4: cm4, 8: cm8}
     km = {}
     if self.conv1_ks != 1:
@@ -136,6 +134,7 @@ class ResUNetEngine:
   def extract(self, xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] = None):
     """K1 -> K2 -> K3 for a batch of clouds (xyz float32 [P,3] on the device, cloud_ptr int64 [n+1]).
     Returns (descriptors [V, out], CoordMap, unique_map): row v describes point xyz[unique_map[v]]."""
-    cm1, umap = ops.voxelize(xyz, voxel, cloud_ptr)
+    cm1, umap = ops.voxelize(xyz, voxel, cloud_ptr, sync=False)
+    maps = self.build_maps(cm1)                     # the only host synchronisation of the forward
     feats = torch.ones((cm1.n, 1), dtype=torch.float32, device=xyz.device)
-    return self.forward(cm1, feats), cm1, umap
+    return self.forward(cm1, feats, maps), cm1, umap[:cm1.n]

@@ -12,10 +12,11 @@ from ._lib import call, ptr, stream, require_cuda
 
 class CoordMap:
   """One coordinate map: int32 rows (b,x,y,z) at a tensor stride + its device hash table."""
-  __slots__ = ("coords", "table", "capacity", "n", "tensor_stride")
+  __slots__ = ("coords", "table", "capacity", "n", "tensor_stride", "status")
 
-  def __init__(self, coords, table, capacity, n, tensor_stride):
+  def __init__(self, coords, table, capacity, n, tensor_stride, status=None):
     self.coords, self.table, self.capacity, self.n, self.tensor_stride = coords, table, capacity, n, tensor_stride
+    self.status = status      # device int32 status word still to be checked (maps built with sync=False)
 
 
 def _new_table(n_rows: int, device) -> Tuple[torch.Tensor, int]:
@@ -51,7 +52,7 @@ def hash_query(cm: CoordMap, q4: torch.Tensor) -> torch.Tensor:
 
 
 def voxelize(xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] = None, return_inverse=False,
-             check: bool = True):
+             check: bool = True, sync: bool = True):
   """K1: sparse_quantize(xyz / voxel) + floor().int() + sparse_collate in one pass
   (lib/complement_data_loader.py:788-789,809-812,1310-1311).
   xyz float32 [P,3] (all clouds concatenated), cloud_ptr int64 [n_clouds+1] (host or device).
@@ -74,6 +75,9 @@ def voxelize(xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] 
   ws = _workspace(lib.gclb_compact_workspace_bytes(P), dev)
   call("gclb_voxelize", ptr(xyz), P, ptr(cloud_ptr), n_clouds, float(voxel), ptr(table), cap, ptr(coords), ptr(umap),
        ptr(inv), ptr(n_out), ptr(status), ptr(ws), stream())
+  if not sync:   # row count and status stay on the device: finish with `finish_maps` (one host read for many maps)
+    cm = CoordMap(coords, table, cap, n_out, 1, status)
+    return (cm, umap, inv) if return_inverse else (cm, umap)
   if check:
     _lib.check_status(status, "voxelize")
   V = int(n_out.item())
@@ -109,27 +113,39 @@ def stride_map(cm: CoordMap, stride: int, return_parent_rows=False, sync: bool =
   new_ts = cm.tensor_stride * stride
   dev = cm.coords.device
   lib = _lib.load()
-  n_in = cm.n
+  n_in_dev = cm.n if isinstance(cm.n, torch.Tensor) else None     # parent not finished yet: chain on the device
+  n_in = cm.coords.shape[0] if n_in_dev is not None else cm.n     # host-side upper bound
   table, cap = _new_table(n_in, dev)
   coords = torch.empty((n_in, 4), dtype=torch.int32, device=dev)
   parent = torch.empty(n_in, dtype=torch.int32, device=dev) if return_parent_rows else None
   n_out = torch.zeros(1, dtype=torch.int64, device=dev)
   status = torch.zeros(1, dtype=torch.int32, device=dev)
   ws = _workspace(lib.gclb_compact_workspace_bytes(n_in), dev)
-  call("gclb_stride_map", ptr(cm.coords), n_in, new_ts, ptr(table), cap, ptr(coords), ptr(parent), ptr(n_out),
-       ptr(status), ptr(ws), stream())
-  out = CoordMap(coords, table, cap, n_out, new_ts)
+  call("gclb_stride_map", ptr(cm.coords), n_in, ptr(n_in_dev), new_ts, ptr(table), cap, ptr(coords), ptr(parent),
+       ptr(n_out), ptr(status), ptr(ws), stream())
+  out = CoordMap(coords, table, cap, n_out, new_ts, status)
   if sync:
-    finish_stride_maps([out])
+    finish_maps([out])
   return (out, parent) if return_parent_rows else out
 
 
-def finish_stride_maps(maps: Sequence[CoordMap]):
-  """One host read for the row counts of several freshly built strided maps."""
-  counts = torch.cat([m.n for m in maps]).tolist()
-  for m, n in zip(maps, counts):
-    m.n = int(n)
+def finish_maps(maps: Sequence[CoordMap]):
+  """ONE host read for the row counts and status words of several maps built with sync=False."""
+  pend = [m for m in maps if isinstance(m.n, torch.Tensor)]
+  if not pend:
+    return
+  vals = torch.cat([m.n for m in pend] + [m.status.to(torch.int64) for m in pend]).tolist()
+  k = len(pend)
+  for i, m in enumerate(pend):
+    st = int(vals[k + i])
+    if st:
+      _lib.check_status(torch.tensor([st]), f"coordinate map (stride {m.tensor_stride})")
+    m.n = int(vals[i])
     m.coords = m.coords[:m.n]
+    m.status = None
+
+
+finish_stride_maps = finish_maps
 
 
 def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1, transposed: bool = False,
@@ -244,32 +260,59 @@ def affine_act(x, scale=None, shift=None, residual=None, relu=False, out=None):
   return out
 
 
-def nn_search(A: torch.Tensor, B: torch.Tensor, a_ptr=None, b_ptr=None, both=True, algo: int = 0):
-  """K4.  Returns (idx01 int64 [N], d01 float32 [N], idx10, d10) with squared-L2 distances; segment-local indices
-  when a_ptr/b_ptr (int64 [n_pairs+1], host lists or tensors) are given."""
-  require_cuda(A, B)
+def subsample(cm: CoordMap, n_clouds: int, S: int, groups: int = 2, seed: int = 0):
+  """Per-cloud random subsample (without replacement) of a batched map's rows, on the device, no host sync.
+  Returns (cloud_ptr int64 [n_clouds+1], sel_ptr int64 [groups, n_clouds/groups+1], sel int64 [groups, n_seg*cap], cap)."""
+  dev = cm.coords.device
+  n_dev = cm.n if isinstance(cm.n, torch.Tensor) else None
+  n_rows = cm.coords.shape[0]
+  cap = S if (S > 0 and S < n_rows) else n_rows
+  n_seg = n_clouds // groups
+  cloud_ptr = torch.empty(n_clouds + 1, dtype=torch.int64, device=dev)
+  sel_ptr = torch.empty((groups, n_seg + 1), dtype=torch.int64, device=dev)
+  sel = torch.empty((groups, max(n_seg * cap, 1)), dtype=torch.int64, device=dev)
+  call("gclb_subsample", ptr(cm.coords), ptr(n_dev), n_rows, n_clouds, S, groups, seed & 0xFFFFFFFFFFFFFFFF,
+       ptr(cloud_ptr), ptr(sel_ptr), ptr(sel), stream())
+  return cloud_ptr, sel_ptr, sel, cap
+
+
+def nn_search(A: torch.Tensor, B: torch.Tensor, a_ptr=None, b_ptr=None, both=True, algo: int = 0, a_rows=None,
+              b_rows=None, max_n: Optional[int] = None, max_m: Optional[int] = None):
+  """K4.  Returns (idx01 int64, d01 float32, idx10, d10, a_ptr_dev, b_ptr_dev, workspace): squared-L2 nearest neighbours
+  in both directions; indices are segment-local when a_ptr/b_ptr (int64 [n_pairs+1]) are given.  With device-resident
+  a_ptr/b_ptr the caller passes max_n/max_m (upper bounds of the segment lengths) and nothing is read back.
+  a_rows/b_rows: optional int64 row indirection (segment row i reads A[a_rows[i]])."""
+  require_cuda(A, B, a_rows, b_rows)
   A, B = A.contiguous(), B.contiguous()
   assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.shape[1] == B.shape[1]
   dev = A.device
-  N, M, Cd = A.shape[0], B.shape[0], A.shape[1]
-  if a_ptr is None:
-    a_host, b_host = [0, N], [0, M]
+  Cd = A.shape[1]
+  if isinstance(a_ptr, torch.Tensor) and a_ptr.is_cuda:
+    assert max_n is not None and max_m is not None, "device-resident segment pointers need max_n / max_m"
+    a_dev, b_dev = a_ptr.contiguous(), b_ptr.contiguous()
+    n_pairs = a_dev.numel() - 1
+    N, M = n_pairs * max_n, n_pairs * max_m
   else:
-    a_host = a_ptr.tolist() if isinstance(a_ptr, torch.Tensor) else list(a_ptr)
-    b_host = b_ptr.tolist() if isinstance(b_ptr, torch.Tensor) else list(b_ptr)
-  n_pairs = len(a_host) - 1
-  max_n = max(a_host[i + 1] - a_host[i] for i in range(n_pairs))
-  max_m = max(b_host[i + 1] - b_host[i] for i in range(n_pairs))
-  a_dev = torch.tensor(a_host, dtype=torch.int64, device=dev)
-  b_dev = torch.tensor(b_host, dtype=torch.int64, device=dev)
+    N = A.shape[0] if a_rows is None else a_rows.numel()
+    M = B.shape[0] if b_rows is None else b_rows.numel()
+    if a_ptr is None:
+      a_host, b_host = [0, N], [0, M]
+    else:
+      a_host = a_ptr.tolist() if isinstance(a_ptr, torch.Tensor) else list(a_ptr)
+      b_host = b_ptr.tolist() if isinstance(b_ptr, torch.Tensor) else list(b_ptr)
+    n_pairs = len(a_host) - 1
+    max_n = max(a_host[i + 1] - a_host[i] for i in range(n_pairs))
+    max_m = max(b_host[i + 1] - b_host[i] for i in range(n_pairs))
+    a_dev = torch.tensor(a_host, dtype=torch.int64, device=dev)
+    b_dev = torch.tensor(b_host, dtype=torch.int64, device=dev)
   lib = _lib.load()
   idx01 = torch.empty(N, dtype=torch.int64, device=dev)
   d01 = torch.empty(N, dtype=torch.float32, device=dev)
   idx10 = torch.empty(M, dtype=torch.int64, device=dev) if both else None
   d10 = torch.empty(M, dtype=torch.float32, device=dev) if both else None
   ws = _workspace(lib.gclb_nn_workspace_bytes(N, M), dev)
-  call("gclb_nn", ptr(A), ptr(B), Cd, ptr(a_dev), ptr(b_dev), n_pairs, N, M, max_n, max_m, ptr(idx01), ptr(d01),
-       ptr(idx10), ptr(d10), algo, ptr(ws), stream())
+  call("gclb_nn", ptr(A), ptr(B), Cd, ptr(a_dev), ptr(b_dev), n_pairs, ptr(a_rows), ptr(b_rows), N, M, max_n, max_m,
+       ptr(idx01), ptr(d01), ptr(idx10), ptr(d10), algo, ptr(ws), stream())
   return idx01, d01, idx10, d10, a_dev, b_dev, ws
 
 

@@ -17,41 +17,27 @@ class PairMatcher:
     self.engine = model if isinstance(model, ResUNetEngine) else ResUNetEngine(model, device=device, algo=algo)
     self.voxel, self.subsample = float(voxel), int(subsample)
     self.device = torch.device(device)
-    self.gen = torch.Generator(device=self.device)
-    self.gen.manual_seed(seed)
+    self.seed, self.calls = int(seed) * 1000003, 0
 
   @torch.no_grad()
   def match(self, xyz: torch.Tensor, cloud_ptr: torch.Tensor):
     """xyz float32 [P,3] (device, or pinned host: copied asynchronously), cloud_ptr int64 [2*n_pairs+1] (host);
     clouds are ordered (pair0.scan0, pair0.scan1, pair1.scan0, ...).
-    Returns dict: pairs int64 [*,2] rows (i, j) = indices into the SUBSAMPLED rows of scan0 / scan1,
-    pair_ptr int64 [n_pairs+1] (device), sel0 / sel1 (voxel rows of the subsample), unique_map (voxel row ->
-    input point), n_voxels (host list per cloud)."""
+    Returns dict (all tensors on the device): pairs int64 [*,2] rows (i, j) = segment-local indices into the SUBSAMPLED
+    rows of scan0 / scan1 of each pair (first pair_ptr[-1] rows valid), pair_ptr int64 [n_pairs+1], a_ptr/b_ptr the CSR
+    of the subsamples, sel0 / sel1 the voxel rows they select (voxel row of pair p's i-th sample = sel0[a_ptr[p] + i]),
+    unique_map (voxel row -> input point), cloud_rows (first voxel row of each cloud), n_voxels_total (host int)."""
     if not xyz.is_cuda:
       xyz = xyz.to(self.device, non_blocking=True)
     n_clouds = cloud_ptr.numel() - 1
     assert n_clouds % 2 == 0, "clouds come in pairs"
     feats, cm, umap = self.engine.extract(xyz, self.voxel, cloud_ptr)
-    # voxel rows are grouped by cloud in order: row range of each cloud from the batch column
-    counts = torch.bincount(cm.coords[:, 0].long(), minlength=n_clouds).tolist()
-    starts = [0]
-    for c in counts:
-      starts.append(starts[-1] + c)
-    S = self.subsample
-    sel = []
-    for c in range(n_clouds):
-      v = counts[c]
-      if S > 0 and v > S:
-        sel.append(torch.randperm(v, device=self.device, generator=self.gen)[:S] + starts[c])
-      else:
-        sel.append(torch.arange(starts[c], starts[c + 1], device=self.device))
-    sel0, sel1 = torch.cat(sel[0::2]), torch.cat(sel[1::2])
-    a_ptr, b_ptr = [0], [0]
-    for p in range(n_clouds // 2):
-      a_ptr.append(a_ptr[-1] + sel[2 * p].numel())
-      b_ptr.append(b_ptr[-1] + sel[2 * p + 1].numel())
-    F0, F1 = feats.index_select(0, sel0), feats.index_select(0, sel1)
-    idx01, d01, idx10, d10, a_dev, b_dev, ws = ops.nn_search(F0, F1, a_ptr, b_ptr, both=True)
+    self.calls += 1
+    n_pairs = n_clouds // 2
+    # per-cloud 5000-row subsample + fused-gather mutual NN, all sizes stay on the device (no host sync)
+    cloud_rows, sel_ptr, sel, cap = ops.subsample(cm, n_clouds, self.subsample, groups=2, seed=self.seed + self.calls)
+    idx01, d01, idx10, d10, a_dev, b_dev, ws = ops.nn_search(feats, feats, sel_ptr[0], sel_ptr[1], both=True,
+                                                             a_rows=sel[0], b_rows=sel[1], max_n=cap, max_m=cap)
     pairs, pair_ptr = ops.mutual_filter(idx01, idx10, a_dev, b_dev, ws)
-    return dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel0, sel1=sel1, a_ptr=a_ptr, b_ptr=b_ptr, idx01=idx01,
-                unique_map=umap, n_voxels=counts, feats=feats, coords=cm.coords)
+    return dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel[0], sel1=sel[1], a_ptr=a_dev, b_ptr=b_dev, idx01=idx01,
+                idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords)

@@ -82,13 +82,15 @@ int gclb_quantize_rows(const int32_t* rows, int64_t P, int32_t width, void* tabl
 /* ------------------------------------------------------------------------------------------------------
  * Strided coordinate map (ME CoordinateManager::stride; model/resunet.py:62-95 stride-2 convolutions):
  * out = unique(floor(c / new_stride) * new_stride), rows ordered by first appearance in the parent map.
+ *   n_in_dev    optional device int64: the true parent row count when only an upper bound n_in is known on the host
+ *               (lets several levels be chained without a host synchronisation)
  *   out_table   hash buffer of gclb_hash_capacity(n_in) slots -> coordinate -> new row
  *   out_coords4 int32 [n_in,4] (first *n_out rows valid);  parent_row_out int32 [n_in] or NULL: new row of
  *   each parent row.
  * ---------------------------------------------------------------------------------------------------- */
-int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, int32_t new_stride, void* out_table,
-                    int64_t out_capacity, int32_t* out_coords4, int32_t* parent_row_out, int64_t* n_out,
-                    int32_t* status, void* workspace, void* stream);
+int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in_dev, int32_t new_stride,
+                    void* out_table, int64_t out_capacity, int32_t* out_coords4, int32_t* parent_row_out,
+                    int64_t* n_out, int32_t* status, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K2 kernel map in output-stationary form ("neighbour table"):
@@ -162,13 +164,28 @@ int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sum
  * sum_c (a_c - b_c)^2 in fp32, ties -> smallest index.
  *   A float32 [sum N_p, C], B float32 [sum M_p, C]; a_ptr/b_ptr int64 [n_pairs+1] device segment starts
  *   (n_pairs independent problems in one launch).  Indices are LOCAL to the segment.
+ *   a_rows / b_rows int64 or NULL: optional row indirection (fused gather): segment row i reads A[a_rows[i]];
+ *   max_n / max_m: upper bounds of the segment lengths (grid sizing; the true lengths are read from a_ptr/b_ptr)
  *   idx01 int64 [sum N], d01 float32 [sum N] ; idx10 int64 [sum M], d10 float32 [sum M] (idx10/d10 may be NULL)
  *   workspace: gclb_nn_workspace_bytes(sum N, sum M)
  * ---------------------------------------------------------------------------------------------------- */
 size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total);
 int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, const int64_t* b_ptr, int32_t n_pairs,
-            int64_t n_total, int64_t m_total, int64_t max_n, int64_t max_m, int64_t* idx01, float* d01,
-            int64_t* idx10, float* d10, int32_t algo, void* workspace, void* stream);
+            const int64_t* a_rows, const int64_t* b_rows, int64_t n_total, int64_t m_total, int64_t max_n,
+            int64_t max_m, int64_t* idx01, float* d01, int64_t* idx10, float* d10, int32_t algo, void* workspace,
+            void* stream);
+/* per-cloud random subsample without replacement of the rows of a batched coordinate map (find_corr's
+ * `np.random.choice(len(F), 5000, replace=False)`, scripts/test_kitti.py:34-35), entirely on the device:
+ *   coords4 int32 [n_rows,4] rows grouped by cloud (column 0 ascending); n_rows_dev optional device int64 row count
+ *   cloud_ptr_out int64 [n_clouds+1] first row of every cloud;
+ *   groups G (1 or 2 ...): cloud c belongs to group c % G as its segment c / G (G = 2: scan 0 / scan 1 of pair c/2);
+ *   sel_ptr_out int64 [G, n_clouds/G + 1]: per group the CSR prefix of min(V_c, S) over its segments;
+ *   sel_out int64 [G, (n_clouds/G) * cap], cap = (S > 0 && S < n_rows) ? S : n_rows: selected GLOBAL row indices, a
+ *   pseudo-random permutation prefix per cloud (S <= 0 or V_c <= S keeps all rows in order).
+ * Feeds gclb_nn directly: a_rows = sel_out[0], a_ptr = sel_ptr_out[0], b_rows = sel_out[1], b_ptr = sel_ptr_out[1]. */
+int gclb_subsample(const int32_t* coords4, const int64_t* n_rows_dev, int64_t n_rows, int32_t n_clouds, int64_t S,
+                   int32_t groups, uint64_t seed, int64_t* cloud_ptr_out, int64_t* sel_ptr_out, int64_t* sel_out,
+                   void* stream);
 /* mutual filter (calculate_M): pairs_out int64 [sum N, 2] = (i, idx01[i]) for rows with idx10[idx01[i]] == i,
  * ascending i inside each segment, segments concatenated; pair_ptr int64 [n_pairs+1] segment starts. */
 int gclb_mutual_filter(const int64_t* idx01, const int64_t* idx10, const int64_t* a_ptr, const int64_t* b_ptr,

@@ -411,6 +411,55 @@ def test_mutual_nn_and_batched_segments(G):
   assert np.array_equal(single, omatch.mutual_nn(As[0], Bs[0])[0])
 
 
+def test_subsample_is_a_sample_without_replacement(G):
+  clouds = [_random_cloud(61, 9000, 20.0), _random_cloud(62, 300, 3.0), _random_cloud(63, 7000, 18.0), _random_cloud(64, 6000, 18.0)]
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(G.dev)
+  ptr = torch.tensor(np.cumsum([0] + [len(c) for c in clouds]))
+  cm, _ = G.ops.voxelize(xyz, 0.3, ptr)
+  counts = torch.bincount(cm.coords[:, 0].long(), minlength=4).tolist()
+  starts = np.cumsum([0] + counts)
+  S = 2000
+  cloud_rows, sel_ptr, sel, cap = G.ops.subsample(cm, 4, S, groups=2, seed=5)
+  assert cloud_rows.tolist() == starts.tolist() and cap == S
+  sp = sel_ptr.cpu().numpy()
+  picked = []
+  for c in range(4):
+    g, sgm = c % 2, c // 2
+    rows = sel[g, sp[g, sgm]:sp[g, sgm + 1]].cpu().numpy()
+    assert len(rows) == min(counts[c], S)
+    assert len(np.unique(rows)) == len(rows)                              # without replacement
+    assert rows.min() >= starts[c] and rows.max() < starts[c + 1]         # inside its own cloud
+    if counts[c] <= S:
+      assert np.array_equal(rows, np.arange(starts[c], starts[c + 1]))    # small clouds are kept whole, in order
+    else:
+      picked.append((rows - starts[c]) / counts[c])
+  # pseudo-random: roughly uniform over the cloud, and a different seed gives a different sample
+  for u in picked:
+    assert abs(u.mean() - 0.5) < 0.03 and abs(np.mean(u < 0.25) - 0.25) < 0.04
+  _, _, sel2, _ = G.ops.subsample(cm, 4, S, groups=2, seed=6)
+  assert not torch.equal(sel, sel2)
+
+
+def test_pair_matcher_pipeline_vs_oracle(G, net):
+  """the public one-call API: correspondences equal the oracle's mutual NN on the same features / same subsample"""
+  om, clouds, C_ref, F_in, ref = net
+  from gcl_b200.pipeline import PairMatcher
+  pm = PairMatcher(om, voxel=0.3, subsample=1500, device=G.dev, seed=3)
+  xyz = torch.from_numpy(np.concatenate(clouds))
+  ptr = torch.tensor([0, len(clouds[0]), len(clouds[0]) + len(clouds[1])])
+  out = pm.match(xyz.pin_memory(), ptr)
+  assert out["n_voxels_total"] == len(C_ref) and torch.equal(out["coords"].cpu(), C_ref)
+  a, b = out["a_ptr"].tolist(), out["b_ptr"].tolist()
+  r0, r1 = out["sel0"][a[0]:a[1]].cpu(), out["sel1"][b[0]:b[1]].cpu()
+  assert len(r0) == 1500 and len(r1) == 1500
+  F = out["feats"].cpu()
+  want, nn01, nn10 = omatch.mutual_nn(F[r0], F[r1])
+  k = int(out["pair_ptr"][-1])
+  got = out["pairs"][:k].cpu().numpy()
+  assert np.array_equal(got, want)
+  assert _rel(F, ref) < FEAT_TOL
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def _loss_inputs(seed, N=6000, G_=900, C=32):
   rng = np.random.RandomState(seed)
