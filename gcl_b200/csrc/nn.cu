@@ -287,8 +287,10 @@ __global__ void __launch_bounds__(256) subsample_kernel(const int64_t* __restric
 }
 
 int nn_tc(const float* A, const float* B, int C, const int64_t* a_ptr, const int64_t* b_ptr, int n_pairs,
-          int64_t max_n, int64_t max_m, unsigned long long* rowbest, unsigned long long* colbest, cudaStream_t st);
+          const int64_t* a_rows, const int64_t* b_rows, int64_t max_n, int64_t max_m, int64_t* idx01, float* d01,
+          int64_t* idx10, float* d10, void* workspace, cudaStream_t st);   // nn_tc.cu
 bool nn_tc_supported(int C);
+size_t nn_tc_workspace_bytes(int n_pairs, int64_t max_n, int64_t max_m);
 
 }  // namespace gclb
 
@@ -296,10 +298,11 @@ using namespace gclb;
 
 extern "C" {
 
-size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total) {
+size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total, int32_t n_pairs, int64_t max_n, int64_t max_m) {
   size_t a = (size_t)(n_total + m_total + 2) * 8;
   size_t b = gclb_compact_workspace_bytes(n_total);
-  return a + b + 64;
+  size_t c = nn_tc_workspace_bytes(n_pairs, max_n, max_m);
+  return (a + b > c ? a + b : c) + 64;
 }
 
 int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, const int64_t* b_ptr, int32_t n_pairs,
@@ -312,25 +315,31 @@ int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, con
   GCLB_CHECK_ARG(n_pairs <= 65535, "too many segments");
   GCLB_CHECK_ARG(algo >= 0 && algo <= 2, "algo must be 0, 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool use_tc = (algo == 2) || (algo == 0 && nn_tc_supported(C));
+  if (use_tc) {
+    if (!nn_tc_supported(C)) {
+      set_error("gclb_nn: C=%d is not covered by the tcgen05 kernel (needs C == 32)", C);
+      return GCLB_ERR_UNSUPPORTED;
+    }
+    if (n_total > 0) cudaMemsetAsync(idx01, 0xff, (size_t)n_total * 8, st);          // rows nobody owns read as -1
+    if (idx10 && m_total > 0) cudaMemsetAsync(idx10, 0xff, (size_t)m_total * 8, st);
+    if (max_n > 0 || max_m > 0) {
+      GCLB_CHECK_ARG(A && B, "null pointer");
+      return nn_tc(A, B, C, a_ptr, b_ptr, n_pairs, a_rows, b_rows, max_n, max_m, idx01, d01, idx10, d10, workspace, st);
+    }
+    GCLB_CHECK_LAUNCH();
+    return GCLB_OK;
+  }
   unsigned long long* rowbest = (unsigned long long*)workspace;
   unsigned long long* colbest = idx10 ? rowbest + n_total : nullptr;
   cudaMemsetAsync(rowbest, 0xff, (size_t)(n_total + (idx10 ? m_total : 0)) * 8, st);
   if (max_n > 0 && max_m > 0) {
     GCLB_CHECK_ARG(B != nullptr, "null pointer");
-    if (algo == 2 || (algo == 0 && nn_tc_supported(C) && false)) {
-      if (!nn_tc_supported(C)) {
-        set_error("gclb_nn: C=%d is not covered by the tcgen05 kernel", C);
-        return GCLB_ERR_UNSUPPORTED;
-      }
-      int r = nn_tc(A, B, C, a_ptr, b_ptr, n_pairs, max_n, max_m, rowbest, colbest, st);
-      if (r != GCLB_OK) return r;
-    } else {
-      dim3 grid((unsigned)((max_m + NT - 1) / NT), (unsigned)((max_n + NT - 1) / NT), (unsigned)n_pairs);
-      GCLB_CHECK_ARG(grid.y <= 65535, "too many row tiles");
-      if (C % 4 == 0) nn_tile_kernel<true><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
-      else nn_tile_kernel<false><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
-      count_launches(1);
-    }
+    dim3 grid((unsigned)((max_m + NT - 1) / NT), (unsigned)((max_n + NT - 1) / NT), (unsigned)n_pairs);
+    GCLB_CHECK_ARG(grid.y <= 65535, "too many row tiles");
+    if (C % 4 == 0) nn_tile_kernel<true><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
+    else nn_tile_kernel<false><<<grid, 256, 0, st>>>(A, B, C, a_ptr, b_ptr, a_rows, b_rows, rowbest, colbest);
+    count_launches(1);
   }
   count_launches((n_total > 0) + (idx10 && m_total > 0));
   if (n_total > 0) nn_unpack_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(rowbest, n_total, idx01, d01);

@@ -310,7 +310,7 @@ def nn_search(A: torch.Tensor, B: torch.Tensor, a_ptr=None, b_ptr=None, both=Tru
   d01 = torch.empty(N, dtype=torch.float32, device=dev)
   idx10 = torch.empty(M, dtype=torch.int64, device=dev) if both else None
   d10 = torch.empty(M, dtype=torch.float32, device=dev) if both else None
-  ws = _workspace(lib.gclb_nn_workspace_bytes(N, M), dev)
+  ws = _workspace(lib.gclb_nn_workspace_bytes(N, M, n_pairs, max_n, max_m), dev)
   call("gclb_nn", ptr(A), ptr(B), Cd, ptr(a_dev), ptr(b_dev), n_pairs, ptr(a_rows), ptr(b_rows), N, M, max_n, max_m,
        ptr(idx01), ptr(d01), ptr(idx10), ptr(d10), algo, ptr(ws), stream())
   return idx01, d01, idx10, d10, a_dev, b_dev, ws

@@ -167,9 +167,12 @@ int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sum
  *   a_rows / b_rows int64 or NULL: optional row indirection (fused gather): segment row i reads A[a_rows[i]];
  *   max_n / max_m: upper bounds of the segment lengths (grid sizing; the true lengths are read from a_ptr/b_ptr)
  *   idx01 int64 [sum N], d01 float32 [sum N] ; idx10 int64 [sum M], d10 float32 [sum M] (idx10/d10 may be NULL)
- *   workspace: gclb_nn_workspace_bytes(sum N, sum M)
+ *   algo: 0 = auto (tcgen05 when C == 32), 1 = exact-fp32 CUDA-core tiles (direct-difference form, any C),
+ *         2 = tcgen05 distance GEMM: operands split exactly into 3 tf32 parts, 6 product groups accumulated in TMEM
+ *             (|a|^2 + |b|^2 - 2 a.b, fp32-exact products); C == 32 only
+ *   workspace: gclb_nn_workspace_bytes(sum N, sum M, n_pairs, max_n, max_m)
  * ---------------------------------------------------------------------------------------------------- */
-size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total);
+size_t gclb_nn_workspace_bytes(int64_t n_total, int64_t m_total, int32_t n_pairs, int64_t max_n, int64_t max_m);
 int gclb_nn(const float* A, const float* B, int32_t C, const int64_t* a_ptr, const int64_t* b_ptr, int32_t n_pairs,
             const int64_t* a_rows, const int64_t* b_rows, int64_t n_total, int64_t m_total, int64_t max_n,
             int64_t max_m, int64_t* idx01, float* d01, int64_t* idx10, float* d10, int32_t algo, void* workspace,

@@ -42,7 +42,7 @@ def test_host_side_helpers(lib):
   assert lib.gclb_hash_capacity(130000) == 262144
   assert lib.gclb_hash_bytes(1024) == 1024 * 12
   assert lib.gclb_compact_workspace_bytes(5000) >= 5000 * 4
-  assert lib.gclb_nn_workspace_bytes(100, 200) >= 300 * 8
+  assert lib.gclb_nn_workspace_bytes(100, 200, 1, 100, 200) >= 300 * 8
 
 
 def test_argument_errors_are_reported_not_crashed(lib):

@@ -388,6 +388,26 @@ def test_nn_vs_oracle(G, n, m, c):
   assert bad.float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("scale", [1.0, 37.5])
+def test_nn_both_kernels_both_directions(G, algo, scale):
+  """fp32 CUDA-core tiles (algo 1) and the tcgen05 3-way-split distance GEMM (algo 2) against the oracle; un-normalised
+  features (scale) make sure nothing assumes unit norms; a planted exact duplicate checks the first-index tie rule."""
+  A, B = _unit(3000, 32, 5) * scale, _unit(4100, 32, 6) * scale
+  B[1234] = B[77]                      # exact tie between candidates 77 and 1234 -> 77 must win
+  A[5] = B[77]
+  idx01, d01, idx10, d10, *_ = G.ops.nn_search(A.to(G.dev), B.to(G.dev), both=True, algo=algo)
+  r01, rd01 = omatch.find_nn(A, B, nn_max_n=500, return_distance=True)
+  r10, rd10 = omatch.find_nn(B, A, nn_max_n=500, return_distance=True)
+  assert idx01[5].item() == 77 and d01[5].item() <= 1e-6 * scale * scale
+  for got, ref, gd, rd, X, Y in ((idx01, r01, d01, rd01, A, B), (idx10, r10, d10, rd10, B, A)):
+    assert torch.allclose(gd.cpu(), rd[:, 0], atol=2e-6 * scale * scale)
+    bad = got.cpu() != ref
+    if bad.any():
+      assert (omatch.nn_margin(X, Y)[bad] < 2e-6 * scale * scale).all()
+    assert bad.float().mean() < 2e-3
+
+
 def test_mutual_nn_and_batched_segments(G):
   sizes = [(900, 1100), (0, 50), (640, 0), (1500, 1300)]
   As = [_unit(n, 32, 10 + i) for i, (n, _) in enumerate(sizes)]
