@@ -4,10 +4,11 @@
 //   one pipeline stage per (populated kernel offset k, 32-channel slab); 4 x tcgen05.mma.kind::tf32 (K = 8) per stage
 //
 // Persistent, warp-specialised CTA (one per SM), 448 threads:
-//   warps 0-7   A producers: gather 128 neighbour rows x 128 B per stage with 16-byte cp.async straight into the canonical
-//               K-major SWIZZLE_128B layout (row r, chunk j -> (r/8)*1024 + (r%8)*128 + ((j ^ (r%8))*16)); missing
-//               neighbours are zero-filled (src-size 0); 3 groups in flight per thread; thread 0 also pulls the weight slab
-//               with ONE cp.async.bulk (the weights are stored pre-swizzled, see gclb_weights_to_tc) onto the same mbarrier.
+//   warps 0-7   A producers, one WARP per ring slot (stage it belongs to warp it % STAGES): gather 128 neighbour rows x 128 B with
+//               16-byte cp.async straight into the canonical K-major SWIZZLE_128B layout (row r, chunk j ->
+//               (r/8)*1024 + (r%8)*128 + ((j ^ (r%8))*16)); missing neighbours are zero-filled (src-size 0); lane 0 also
+//               pulls the weight slab with ONE cp.async.bulk (weights are stored pre-swizzled, see gclb_weights_to_tc)
+//               onto the same mbarrier.  Each warp waits only for its own stage => up to 8 stages in flight per SM.
 //   warp  8     one elected thread issues tcgen05.mma; tcgen05.commit recycles smem slots and publishes accumulators.
 //   warp  9     prefetches the next tile's slice of the neighbour table (cp.async) and lists its populated offsets.
 //   warps 10-13 epilogue: tcgen05.ld (thread <-> output row), fused scale/shift (+residual) (+ReLU) (+L2 normalise),
@@ -21,10 +22,8 @@ namespace gclb {
 constexpr int KSLAB = 32;             // channels per stage = one 128-byte swizzle row
 constexpr int A_BYTES = TM * 128;     // 16 KB
 constexpr int kGatherWarps = 8;
-constexpr int kGatherThreads = kGatherWarps * 32;   // 256
 constexpr int kMmaWarp = 8, kNbrWarp = 9;
 constexpr int kTcThreads = 14 * 32;   // 448: warps 10-13 are the epilogue
-constexpr int kInFlight = 3;          // cp.async groups in flight per producer thread
 
 template <int COUT>
 struct TcCfg {
@@ -61,12 +60,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
 
   if (tid == 0) {
     if ((smem_u32(ring) & 1023u) != 0) { printf("gclb spconv_tc: operand ring not 1024-byte aligned\n"); __trap(); }
-    for (int s = 0; s < S; ++s) { mbar_init(&sh.full[s], kGatherThreads + 1); mbar_init(&sh.empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&sh.full[s], 2); mbar_init(&sh.empty[s], 1); }   // expect_tx + data-landed
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh.acc_full[b], 1);
       mbar_init(&sh.acc_empty[b], 4);
       mbar_init(&sh.nbr_full[b], 1);
-      mbar_init(&sh.nbr_empty[b], kGatherWarps + 1 + 4);
+      mbar_init(&sh.nbr_empty[b], (S < kGatherWarps ? S : kGatherWarps) + 1 + 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -83,67 +82,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   const uint32_t ring_u32 = smem_u32(ring);
 
   if (warp < kGatherWarps) {
-    // ======================================= A producers (+ weight bulk copy by thread 0) =================
-    const int j = tid & 7;            // 16-byte chunk inside the 128-byte row
-    const int r0 = tid >> 3;          // rows r0, r0+32, r0+64, r0+96
-    uint32_t dst_off[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = r0 + 32 * q;
-      dst_off[q] = (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4);
-    }
-    uint32_t issued = 0, arrived = 0;
+    if (warp < S) {
+    // ======================================= A producers: one WARP per pipeline stage ========================
+    // Warp w owns ring slot w (stages it with it % S == w; S <= 8): it gathers the whole 128 x 128 B slab (32 cp.async per
+    // lane), pulls the weight slab with one bulk copy, then waits for ITS OWN data only (wait_group 0 + proxy fence)
+    // and arrives.  Eight warps => up to eight stages in flight per SM; no thread ever stalls behind another stage.
+    const int j = lane & 7;           // 16-byte chunk inside the 128-byte row
+    const int rq = lane >> 3;         // rows rq + 4*q, q = 0..31
+    uint32_t it = 0;                  // global stage counter (identical in every role)
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int b = lt & 1;
       const int64_t tile_m = (int64_t)tile * TM;
       mbar_wait(&sh.nbr_full[b], (lt >> 1) & 1);
       const int* nb = nbr_buf + b * NBR_INTS;
-      const int n_act = sh.n_act[b];
-      for (int ai = 0; ai < n_act; ++ai) {
-        const int k = sh.act_k[b][ai];
-        int idx[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = r0 + 32 * q;
-          if (identity) idx[q] = (tile_m + r < p.n_out) ? (int)(tile_m + r) : -1;
-          else idx[q] = nb[r * KVOL + k];
+      const int n_iter = sh.n_act[b] * slabs;
+      for (int i = 0; i < n_iter; ++i, ++it) {
+        if ((int)(it % S) != warp) continue;              // ring slot s is always filled by warp s (S <= 8 warps active):
+                                                          // successive rounds of a slot are ordered => no mbarrier phase aliasing
+        const int k = sh.act_k[b][i / slabs];
+        const int c = (i % slabs) * KSLAB;
+        const int stage = it % S;
+        mbar_wait(&sh.empty[stage], ((it / S) & 1u) ^ 1u);   // passes immediately during the first round
+        const float* src_base;
+        int src_stride;
+        if (c < p.c0) { src_base = p.in0 + c + j * 4; src_stride = p.c0; }
+        else { src_base = p.in1 + (c - p.c0) + j * 4; src_stride = p.c1; }
+        const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
+        if (lane == 0) {   // weight slab: one bulk copy of the pre-swizzled image
+          mbar_arrive_expect_tx(&sh.full[stage], Cfg::B_BYTES);
+          bulk_g2s(a_s + A_BYTES, p.W + ((size_t)k * slabs + c / KSLAB) * (COUT * KSLAB), Cfg::B_BYTES, &sh.full[stage]);
         }
-        for (int sl = 0; sl < slabs; ++sl) {
-          const int stage = issued % S;
-          mbar_wait(&sh.empty[stage], ((issued / S) & 1u) ^ 1u);   // passes immediately during the first round
-          const int c = sl * KSLAB;
-          const float* src_base;
-          int src_stride;
-          if (c < p.c0) { src_base = p.in0 + c + j * 4; src_stride = p.c0; }
-          else { src_base = p.in1 + (c - p.c0) + j * 4; src_stride = p.c1; }
-          const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
-          if (tid == 0) {   // weight slab: one bulk copy of the pre-swizzled image
-            mbar_arrive_expect_tx(&sh.full[stage], Cfg::B_BYTES);
-            bulk_g2s(a_s + A_BYTES, p.W + ((size_t)k * slabs + sl) * (COUT * KSLAB), Cfg::B_BYTES, &sh.full[stage]);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const bool ok = idx[q] >= 0;
-            cp_async16(a_s + dst_off[q], ok ? (const void*)(src_base + (size_t)idx[q] * src_stride) : (const void*)p.in0,
-                       ok ? 16u : 0u);
-          }
-          cp_async_commit();
-          ++issued;
-          if (issued - arrived > kInFlight - 1) {   // the oldest outstanding group has landed
-            cp_async_wait<kInFlight - 1>();
-            fence_proxy_async();
-            mbar_arrive(&sh.full[arrived % S]);
-            ++arrived;
-          }
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+          const int r = rq + 4 * q;
+          int idx;
+          if (identity) idx = (tile_m + r < p.n_out) ? (int)(tile_m + r) : -1;
+          else idx = nb[r * KVOL + k];
+          const bool ok = idx >= 0;
+          const uint32_t dst = a_s + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4);
+          cp_async16(dst, ok ? (const void*)(src_base + (size_t)idx * src_stride) : (const void*)p.in0, ok ? 16u : 0u);
         }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.full[stage]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.nbr_empty[b]);   // this warp no longer reads the neighbour tile
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (arrived < issued) { mbar_arrive(&sh.full[arrived % S]); ++arrived; }
+    }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer (one thread) =======================================
     if (lane == 0) {

@@ -195,6 +195,28 @@ def test_tc_dense_pointwise_gemm(G, n, cin, cout):
   assert torch.equal(got.cpu(), xi @ Wi[0])
 
 
+def test_tc_persistent_many_tiles(G):
+  """more 128-row tiles than SMs (several tiles per persistent CTA), for short (K = 1, 2-3 stages per tile) and long
+  (K = 27) tiles: exercises ring wrap-around, accumulator double-buffering and the deferred-arrival drain"""
+  torch.manual_seed(14)
+  n = 148 * 128 * 5 + 77
+  for cin, cout in ((64, 32), (96, 64), (32, 32)):
+    x = torch.randint(-3, 4, (n, cin)).float()
+    W = torch.randint(-3, 4, (1, cin, cout)).float()
+    got = G.ops.spconv_fwd(x.to(G.dev), G.ops.weights_to_tc(W.to(G.dev)), None, n, algo=2)
+    assert torch.equal(got.cpu(), x @ W[0])
+  cloud = np.concatenate([_random_cloud(70 + i, 30000, 60.0) + np.array([200.0 * i, 0, 0], np.float32) for i in range(3)])
+  cm, _ = G.ops.voxelize(torch.from_numpy(cloud).to(G.dev), 0.3)
+  assert cm.n > 148 * 128 * 3
+  nbr = G.ops.kernel_map(cm, cm, 3)
+  x = torch.randint(-2, 3, (cm.n, 64), device=G.dev).float()
+  W = torch.randint(-2, 3, (27, 64, 64), device=G.dev).float()
+  ref = G.ops.spconv_fwd(x, W, nbr, cm.n, algo=1)           # exact-fp32 kernel; integer data => both are exact
+  srt, perm = G.ops.kernel_map_sort(nbr)
+  got = G.ops.spconv_fwd(x, G.ops.weights_to_tc(W), srt, cm.n, algo=2, row_perm=perm)
+  assert torch.equal(got, ref)
+
+
 def test_tc_fused_l2_normalise_tail(G):
   torch.manual_seed(8)
   n = 3001
