@@ -37,6 +37,7 @@ struct ConvParams {   // sparse-conv forward arguments shared by the fp32 (spcon
   int K, cout;
   const int32_t* nbr;
   const int32_t* perm;   // tcgen05 path: table row t describes output row perm[t] (NULL = identity)
+  const uint32_t* tile_mask;   // tcgen05 path: per 128-row tile, bit k set iff offset k is populated (NULL = scan)
   const float* scale; const float* shift; const float* residual;
   int relu;
   float* out;

@@ -129,12 +129,21 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uin
 }
 
 __global__ void __launch_bounds__(256) permute_rows_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ perm,
-                                                           int64_t n, int K, int32_t* __restrict__ out) {
+                                                           int64_t n, int K, int32_t* __restrict__ out,
+                                                           uint32_t* __restrict__ tile_mask) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t t = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * wpb) {
     const int64_t o = perm[t];
-    for (int k = lane; k < K; k += 32) out[t * K + k] = __ldg(&nbr[o * K + k]);
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      int v = -1;
+      if (k < K) { v = __ldg(&nbr[o * K + k]); out[t * K + k] = v; }
+      if (tile_mask && k0 == 0) {      // K <= 32: which offsets are populated anywhere in the 128-row tile
+        unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+        if (lane == 0 && m) atomicOr(&tile_mask[t >> 7], m);
+      }
+    }
   }
 }
 
@@ -190,7 +199,7 @@ size_t gclb_kmap_sort_workspace_bytes(int64_t n_out) {
 }
 
 int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_t* perm_out, int32_t* nbr_sorted_out,
-                        void* workspace, void* stream) {
+                        uint32_t* tile_mask_out, void* workspace, void* stream) {
   GCLB_CHECK_ARG(workspace && ksize >= 1 && ksize <= 7, "bad arguments");
   if (n_out == 0) return GCLB_OK;
   GCLB_CHECK_ARG(nbr && perm_out && nbr_sorted_out, "null pointer");
@@ -205,7 +214,11 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_
   rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out);
   int64_t blocks = (n_out + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-  permute_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out);
+  if (tile_mask_out) {
+    GCLB_CHECK_ARG(K <= 32, "tile masks need ksize^3 <= 32");
+    cudaMemsetAsync(tile_mask_out, 0, (size_t)((n_out + 127) / 128) * 4, st);
+  }
+  permute_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
   count_launches(4);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -322,9 +322,9 @@ using namespace gclb;
 extern "C" {
 
 int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
-                    int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const float* scale,
-                    const float* shift, const float* residual, int32_t relu, float* out, int64_t n_out, int32_t algo,
-                    void* stream) {
+                    int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
+                    const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                    int64_t n_out, int32_t algo, void* stream) {
   GCLB_CHECK_ARG(W && (n_out == 0 || out), "null pointer");
   GCLB_CHECK_ARG(c0 >= 1 && c1 >= 0 && K >= 1 && cout >= 1, "bad shape");
   GCLB_CHECK_ARG((c1 == 0) == (in1 == nullptr), "in1 / c1 mismatch");
@@ -334,9 +334,10 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
   GCLB_CHECK_ARG(relu >= 0 && relu <= 3, "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows (tcgen05 path, cout == 32)");
   GCLB_CHECK_ARG(algo == 2 || (relu & 2) == 0, "the fused L2 normalise exists on the tcgen05 path only");
   GCLB_CHECK_ARG(row_perm == nullptr || (algo == 2 && nbr != nullptr), "row_perm is a tcgen05-path option and needs nbr");
+  GCLB_CHECK_ARG(tile_mask == nullptr || (algo == 2 && nbr != nullptr && K <= 32), "tile_mask is a tcgen05-path option");
   if (n_out == 0) return GCLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  ConvParams p{in0, in1, c0, c1, W, K, cout, nbr, row_perm, scale, shift, residual, relu, out, n_out};
+  ConvParams p{in0, in1, c0, c1, W, K, cout, nbr, row_perm, tile_mask, scale, shift, residual, relu, out, n_out};
   const int cin = c0 + c1;
   cudaError_t e;
   if (algo == 2) {   // W is in the tensor-core layout [K][cout][cin]

@@ -31,27 +31,31 @@ struct TcCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   // deepest ring that leaves room for two neighbour tiles (2 x 14 KB) in 227 KB
   static constexpr int STAGES = COUT >= 256 ? 4 : (COUT >= 128 ? 5 : (COUT >= 64 ? 7 : 8));
-  static constexpr int TMEM_COLS = 2 * (COUT < 32 ? 32 : COUT);   // double-buffered accumulator (power of two >= 64)
+  static constexpr int NBUF = COUT >= 256 ? 2 : 4;                // neighbour-tile ring (tiles prefetched ahead)
+  static constexpr int NACC = COUT >= 256 ? 2 : 4;                // TMEM accumulator ring (tiles the MMA may run ahead)
+  static constexpr int TMEM_COLS = NACC * COUT;                   // 128 / 256 / 512 / 512 columns (powers of two)
 };
 
 struct TcShared {   // static shared: barriers + small per-tile metadata
   uint64_t full[8], empty[8];
-  uint64_t acc_full[2], acc_empty[2];
-  uint64_t nbr_full[2], nbr_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
+  uint64_t nbr_full[4], nbr_empty[4];
   uint32_t tmem_base;
-  int n_act[2];
-  int act_k[2][32];
+  int n_act[4];
+  int acc_n_act[4];        // per accumulator: number of populated offsets of the tile it holds (0 => treat as zeros)
+  int act_k[4][32];
 };
 
 template <int COUT, int KVOL>
 __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize) {
   using Cfg = TcCfg<COUT>;
   constexpr int S = Cfg::STAGES;
+  constexpr int NBUF = Cfg::NBUF, NACC = Cfg::NACC;
   constexpr int NBR_INTS = TM * KVOL;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ TcShared sh;
   unsigned char* ring = smem_dyn;
-  int* nbr_buf = reinterpret_cast<int*>(smem_dyn + S * Cfg::STAGE);    // [2][NBR_INTS]
+  int* nbr_buf = reinterpret_cast<int*>(smem_dyn + S * Cfg::STAGE);    // [NBUF][NBR_INTS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cin = p.c0 + p.c1;
@@ -61,11 +65,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   if (tid == 0) {
     if ((smem_u32(ring) & 1023u) != 0) { printf("gclb spconv_tc: operand ring not 1024-byte aligned\n"); __trap(); }
     for (int s = 0; s < S; ++s) { mbar_init(&sh.full[s], 2); mbar_init(&sh.empty[s], 1); }   // expect_tx + data-landed
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&sh.acc_full[b], 1);
       mbar_init(&sh.acc_empty[b], 4);
       mbar_init(&sh.nbr_full[b], 1);
-      mbar_init(&sh.nbr_empty[b], (S < kGatherWarps ? S : kGatherWarps) + 1 + 4);
+      mbar_init(&sh.nbr_empty[b], (S < kGatherWarps ? S : kGatherWarps) + 1);   // gather warps + MMA thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -92,9 +96,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
     uint32_t it = 0;                  // global stage counter (identical in every role)
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int b = lt & 1;
+      const int b = lt % NBUF;
       const int64_t tile_m = (int64_t)tile * TM;
-      mbar_wait(&sh.nbr_full[b], (lt >> 1) & 1);
+      mbar_wait(&sh.nbr_full[b], (lt / NBUF) & 1);
       const int* nb = nbr_buf + b * NBR_INTS;
       const int n_iter = sh.n_act[b] * slabs;
       for (int i = 0; i < n_iter; ++i, ++it) {
@@ -140,13 +144,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
       uint32_t it = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int b = lt & 1;
-        mbar_wait(&sh.nbr_full[b], (lt >> 1) & 1);
-        const int n_iter = sh.n_act[b] * slabs;
+        const int b = lt % NBUF, ab = lt % NACC;
+        mbar_wait(&sh.nbr_full[b], (lt / NBUF) & 1);
+        const int n_act = sh.n_act[b];
+        const int n_iter = n_act * slabs;
         mbar_arrive(&sh.nbr_empty[b]);
-        mbar_wait(&sh.acc_empty[b], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        mbar_wait(&sh.acc_empty[ab], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * COUT);
+        *reinterpret_cast<volatile int*>(&sh.acc_n_act[ab]) = n_act;   // read by the epilogue after acc_full
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * COUT);
         for (int i = 0; i < n_iter; ++i, ++it) {
           const int stage = it % S;
           mbar_wait(&sh.full[stage], (it / S) & 1u);
@@ -158,16 +164,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
             umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
           umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
         }
-        if (n_iter > 0) umma_commit(&sh.acc_full[b]);
-        else mbar_arrive(&sh.acc_full[b]);
+        if (n_iter > 0) umma_commit(&sh.acc_full[ab]);
+        else mbar_arrive(&sh.acc_full[ab]);
       }
     }
   } else if (warp == kNbrWarp) {
     // ======================================= neighbour-tile prefetch ========================================
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int b = lt & 1;
-      mbar_wait(&sh.nbr_empty[b], ((lt >> 1) & 1) ^ 1);
+      const int b = lt % NBUF;
+      mbar_wait(&sh.nbr_empty[b], ((lt / NBUF) & 1) ^ 1);
       int* nb = nbr_buf + b * NBR_INTS;
       int n_act = 1;
       if (identity) {
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           cp_async16(nb_u32 + ch * 16, bytes ? (const void*)(p.nbr + e) : (const void*)p.nbr, bytes);
         }
         cp_async_commit();
+        unsigned m = p.tile_mask ? __ldg(p.tile_mask + tile) : 0u;       // populated offsets, precomputed at sort time
         cp_async_wait<0>();
         __syncwarp();
         const int64_t rows_left = p.n_out - (int64_t)tile * TM;
@@ -191,12 +198,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           for (int e = rows * KVOL + lane; e < NBR_INTS; e += 32) nb[e] = -1;
           __syncwarp();
         }
-        int f = 0;         // which offsets have at least one neighbour in this tile
-        if (lane < KVOL) {
+        if (!p.tile_mask) {   // no precomputed mask: scan the tile (one lane per offset)
+          int f = 0;
+          if (lane < KVOL) {
 #pragma unroll 8
-          for (int r = 0; r < rows; ++r) f |= (nb[r * KVOL + lane] >= 0);
+            for (int r = 0; r < rows; ++r) f |= (nb[r * KVOL + lane] >= 0);
+          }
+          m = __ballot_sync(0xffffffffu, f);
         }
-        unsigned m = __ballot_sync(0xffffffffu, f);
+        const int f = (m >> lane) & 1u;
         if (f) sh.act_k[b][__popc(m & ((1u << lane) - 1))] = lane;
         n_act = __popc(m);
       }
@@ -210,34 +220,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
     const int row = quarter * 32 + lane;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int b = lt & 1;
-      mbar_wait(&sh.nbr_full[b], (lt >> 1) & 1);
-      const bool empty_tile = (sh.n_act[b] == 0);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.nbr_empty[b]);
-      mbar_wait(&sh.acc_full[b], (lt >> 1) & 1);
-      tc_fence_after();
+      const int ab = lt % NACC;
+      // everything that does not depend on the accumulator is fetched BEFORE waiting for it: the output row id and
+      // the first 32 residual values, so their DRAM latency overlaps the tile's main loop
       const int64_t t_row = (int64_t)tile * TM + row;
       int64_t o = p.n_out;                                   // rows past the end are never stored
       if (t_row < p.n_out) o = p.perm ? (int64_t)__ldg(p.perm + t_row) : t_row;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * COUT);
+      const bool live = o < p.n_out;
+      const float* res = (p.residual && live) ? p.residual + (size_t)o * COUT : nullptr;
+      float4 rc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&sh.acc_full[ab], (lt / NACC) & 1);
+      tc_fence_after();
+      const bool empty_tile = (*reinterpret_cast<volatile int*>(&sh.acc_n_act[ab]) == 0);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * COUT);
 #pragma unroll 1
       for (int n0 = 0; n0 < COUT; n0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)n0, v);
-        if (n0 + 32 >= COUT) {                         // last TMEM read of this tile: hand the accumulator back
+        float4 rn[8];                                       // residual of the NEXT 32 columns, in flight during this chunk
+        const bool more = (n0 + 32 < COUT);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          rn[q] = (more && res) ? __ldg(reinterpret_cast<const float4*>(res + n0 + 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!more) {                                        // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.acc_empty[b]);
+          if (lane == 0) mbar_arrive(&sh.acc_empty[ab]);
         }
-        if (o < p.n_out) {
+        if (live) {
           float y[32];
-          const float* res = p.residual ? p.residual + (size_t)o * COUT + n0 : nullptr;
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
             float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q)) : make_float4(1.f, 1.f, 1.f, 1.f);
             float4 sf = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 r = res ? __ldg(reinterpret_cast<const float4*>(res + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 r = rc[q >> 2];
             y[q + 0] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 0]), sc.x, sf.x) + r.x;
             y[q + 1] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 1]), sc.y, sf.y) + r.y;
             y[q + 2] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 2]), sc.z, sf.z) + r.z;
@@ -259,6 +277,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
 #pragma unroll
           for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rc[q] = rn[q];
       }
     }
   }
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(256) weights_to_tc_kernel(const float* __restr
 template <int COUT, int KVOL>
 static int launch_tc(const ConvParams& p, cudaStream_t st) {
   using Cfg = TcCfg<COUT>;
-  size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)2 * TM * KVOL * 4;
+  size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
   auto kern = spconv_fwd_tc_kernel<COUT, KVOL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {

@@ -74,11 +74,11 @@ class ResUNetEngine:
   def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False):
     W, sc, sh = self.p[key]
     if key in self.tc:
-      perm = None
-      if isinstance(nbr, tuple):          # (table, sorted table, perm) from build_maps
-        nbr, perm = nbr[1], nbr[2]
+      perm = mask = None
+      if isinstance(nbr, tuple):          # (table, sorted table, perm, tile masks) from build_maps
+        nbr, perm, mask = nbr[1], nbr[2], nbr[3]
       return ops.spconv_fwd(x, self.tc[key], nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
-                            algo=2, row_perm=perm)
+                            algo=2, row_perm=perm, tile_mask=mask)
     if isinstance(nbr, tuple):
       nbr = nbr[0]
     return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)

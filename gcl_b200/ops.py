@@ -177,23 +177,24 @@ def kernel_map_pairs(nbr: torch.Tensor):
 
 
 def kernel_map_sort(nbr: torch.Tensor):
-  """Group table rows by neighbour-direction pattern for the tcgen05 kernel: returns (nbr_sorted, perm) with
-  nbr_sorted[t] = nbr[perm[t]]."""
+  """Group table rows by neighbour-direction pattern for the tcgen05 kernel: returns (nbr_sorted, perm, tile_mask) with
+  nbr_sorted[t] = nbr[perm[t]] and tile_mask[t // 128] = bit mask of the offsets populated in that 128-row tile."""
   n_out, K = nbr.shape
   ksize = round(K ** (1 / 3))
   assert ksize ** 3 == K
   lib = _lib.load()
   perm = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
   out = torch.empty_like(nbr)
+  mask = torch.empty((n_out + 127) // 128, dtype=torch.int32, device=nbr.device) if K <= 32 else None
   ws = _workspace(lib.gclb_kmap_sort_workspace_bytes(n_out), nbr.device)
-  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(perm), ptr(out), ptr(ws), stream())
-  return out, perm
+  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(perm), ptr(out), ptr(mask), ptr(ws), stream())
+  return out, perm, mask
 
 
 def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
                out: Optional[torch.Tensor] = None, algo: int = 0, normalize: bool = False,
-               row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+               row_perm: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
   """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path); with algo=2 (tcgen05) W is the
   tensor-core layout [K, Cout, Cin] from `weights_to_tc`."""
   require_cuda(in0, W, nbr, in1, scale, shift, residual)
@@ -212,7 +213,7 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   if out is None:
     out = torch.empty((n_out, cout), dtype=torch.float32, device=in0.device)
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
-       ptr(row_perm), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)) | (2 if normalize else 0), ptr(out), n_out, algo,
+       ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)) | (2 if normalize else 0), ptr(out), n_out, algo,
        stream())
   return out
 

@@ -111,11 +111,12 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
                     int64_t* offset_ptr, void* workspace, void* stream);
 
 /* group the rows of a neighbour table by a 6-bit neighbour-direction key (stable counting sort): perm_out int32 [n_out]
- * (sorted position -> original row), nbr_sorted_out int32 [n_out, ksize^3] = nbr[perm_out].  Pure re-ordering: pass
+ * (sorted position -> original row), nbr_sorted_out int32 [n_out, ksize^3] = nbr[perm_out]; tile_mask_out uint32
+ * [ceil(n_out/128)] or NULL (ksize^3 <= 32): bit k set iff offset k is populated in that 128-row tile.  Pure re-ordering: pass
  * both to gclb_spconv_fwd(algo=2); results are identical, the kernel just runs ~2-8x fewer pipeline stages. */
 size_t gclb_kmap_sort_workspace_bytes(int64_t n_out);
 int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_t* perm_out, int32_t* nbr_sorted_out,
-                        void* workspace, void* stream);
+                        uint32_t* tile_mask_out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K3 sparse convolution forward, output-stationary implicit GEMM with fused epilogue
@@ -127,6 +128,8 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_
  *   nbr int32 [n_out, K] or NULL (K==1: identity map, the kernel_size==1 `F.mm` path)
  *   row_perm int32 [n_out] or NULL: tcgen05 path only -- row t of `nbr` then describes OUTPUT row row_perm[t]
  *            (tables re-ordered by gclb_kmap_sort_rows so that a 128-row tile touches few kernel offsets)
+ *   tile_mask uint32 [ceil(n_out/128)] or NULL: tcgen05 path only -- populated-offset bit mask per 128-row tile of
+ *            `nbr` (from gclb_kmap_sort_rows); saves the kernel an in-tile scan
  *   scale, shift float32 [cout] or NULL    : folded eval-mode BatchNorm / bias
  *   residual float32 [n_out, cout] or NULL ; relu: bit 0 = ReLU, bit 1 = divide every output row by its L2 norm
  *   afterwards (model/resunet.py:226-230; tcgen05 path with cout == 32 only)
@@ -140,9 +143,9 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_
  * (done once per layer; needs cin % 32 == 0, cout % 8 == 0) */
 int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream);
 int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
-                    int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const float* scale,
-                    const float* shift, const float* residual, int32_t relu, float* out, int64_t n_out, int32_t algo,
-                    void* stream);
+                    int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
+                    const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                    int64_t n_out, int32_t algo, void* stream);
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
                       const int32_t* nbr, int32_t K, float* gW, void* stream);

@@ -48,7 +48,7 @@ def test_host_side_helpers(lib):
 def test_argument_errors_are_reported_not_crashed(lib):
   rc = lib.gclb_hash_build(None, 1024, None, 10, None, None)
   assert rc == -1 and b"null" in lib.gclb_last_error()
-  rc = lib.gclb_spconv_fwd(None, 0, None, 0, 0, None, 1, 1, None, None, None, None, None, 0, None, 0, 0, None)
+  rc = lib.gclb_spconv_fwd(None, 0, None, 0, 0, None, 1, 1, None, None, None, None, None, None, 0, None, 0, 0, None)
   assert rc == -1
 
 

@@ -212,9 +212,12 @@ def test_tc_persistent_many_tiles(G):
   x = torch.randint(-2, 3, (cm.n, 64), device=G.dev).float()
   W = torch.randint(-2, 3, (27, 64, 64), device=G.dev).float()
   ref = G.ops.spconv_fwd(x, W, nbr, cm.n, algo=1)           # exact-fp32 kernel; integer data => both are exact
-  srt, perm = G.ops.kernel_map_sort(nbr)
-  got = G.ops.spconv_fwd(x, G.ops.weights_to_tc(W), srt, cm.n, algo=2, row_perm=perm)
+  srt, perm, mask = G.ops.kernel_map_sort(nbr)
+  got = G.ops.spconv_fwd(x, G.ops.weights_to_tc(W), srt, cm.n, algo=2, row_perm=perm, tile_mask=mask)
   assert torch.equal(got, ref)
+  res = torch.randint(-2, 3, (cm.n, 64), device=G.dev).float()
+  got = G.ops.spconv_fwd(x, G.ops.weights_to_tc(W), srt, cm.n, algo=2, row_perm=perm, tile_mask=mask, residual=res, relu=True)
+  assert torch.equal(got, torch.relu(ref + res))
 
 
 def test_tc_fused_l2_normalise_tail(G):
@@ -236,7 +239,7 @@ def test_kmap_row_bucketing_is_a_pure_reordering(G):
   cm = G.ops.hash_build(C_ref.to(G.dev))
   cm2 = G.ops.stride_map(cm, 2)
   for nbr in (G.ops.kernel_map(cm, cm, 3), G.ops.kernel_map(cm2, cm, 3, transposed=True), G.ops.kernel_map(cm, cm2, 3)):
-    srt, perm = G.ops.kernel_map_sort(nbr)
+    srt, perm, mask = G.ops.kernel_map_sort(nbr)
     n = nbr.shape[0]
     assert torch.equal(torch.sort(perm.long()).values.cpu(), torch.arange(n))
     assert torch.equal(srt, nbr[perm.long()])
@@ -254,7 +257,10 @@ def test_kmap_row_bucketing_is_a_pure_reordering(G):
     Wt = G.ops.weights_to_tc(W)
     a = G.ops.spconv_fwd(x, Wt, nbr, n, algo=2)
     b = G.ops.spconv_fwd(x, Wt, srt, n, algo=2, row_perm=perm)
-    assert torch.equal(a, b)
+    c = G.ops.spconv_fwd(x, Wt, srt, n, algo=2, row_perm=perm, tile_mask=mask)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    want_mask = [int(sum(1 << k for k in range(27) if v[t:t + 128, k].any())) for t in range(0, n, 128)]
+    assert mask.tolist() == want_mask
 
 
 def test_tc_two_source_epilogue(G):
