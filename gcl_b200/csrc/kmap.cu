@@ -7,7 +7,8 @@ namespace gclb {
 
 __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int32_t* __restrict__ out_c4,
                                                          int64_t n_out, int ksize, int K, int step, int sign,
-                                                         int32_t* __restrict__ nbr, int32_t* __restrict__ pair_count) {
+                                                         int32_t* __restrict__ nbr, int32_t* __restrict__ pair_count,
+                                                         uint8_t* __restrict__ row_keys) {
   extern __shared__ int s_count[];  // [K]
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_count[k] = 0;
   __syncthreads();
@@ -17,15 +18,30 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
   for (int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); o < n_out;
        o += (int64_t)gridDim.x * warps_per_block) {
     int4 c = __ldg(reinterpret_cast<const int4*>(out_c4) + o);
-    for (int k = lane; k < K; k += 32) {
-      int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
-      int x = c.y + sign * (ix - half) * step;
-      int y = c.z + sign * (iy - half) * step;
-      int z = c.w + sign * (iz - half) * step;
-      int r = coord_in_range(c.x, x, y, z) ? hash_find(t, pack_key(c.x, x, y, z)) : -1;
-      nbr[o * K + k] = r;
-      if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
+    int key = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      int r = -1, ix = 0, iy = 0, iz = 0;
+      if (k < K) {
+        ix = k % ksize; iy = (k / ksize) % ksize; iz = k / (ksize * ksize);
+        int x = c.y + sign * (ix - half) * step;
+        int y = c.z + sign * (iy - half) * step;
+        int z = c.w + sign * (iz - half) * step;
+        r = coord_in_range(c.x, x, y, z) ? hash_find(t, pack_key(c.x, x, y, z)) : -1;
+        nbr[o * K + k] = r;
+        if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
+      }
+      if (row_keys) {   // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
+        const bool v = r >= 0;
+        key |= __ballot_sync(0xffffffffu, v && ix < half) ? 1 : 0;
+        key |= __ballot_sync(0xffffffffu, v && ix > half) ? 2 : 0;
+        key |= __ballot_sync(0xffffffffu, v && iy < half) ? 4 : 0;
+        key |= __ballot_sync(0xffffffffu, v && iy > half) ? 8 : 0;
+        key |= __ballot_sync(0xffffffffu, v && iz < half) ? 16 : 0;
+        key |= __ballot_sync(0xffffffffu, v && iz > half) ? 32 : 0;
+      }
     }
+    if (row_keys && lane == 0) row_keys[o] = (uint8_t)key;
   }
   __syncthreads();
   if (pair_count)
@@ -92,14 +108,15 @@ __device__ __forceinline__ int row_key(const int32_t* __restrict__ row, int ksiz
 }
 
 __global__ void __launch_bounds__(kCompactBlock) rowkey_hist_kernel(const int32_t* __restrict__ nbr, int64_t n, int ksize,
-                                                                    int K, uint8_t* __restrict__ keys,
+                                                                    int K, const uint8_t* __restrict__ keys_in,
+                                                                    uint8_t* __restrict__ keys,
                                                                     int32_t* __restrict__ hist, int64_t nblocks) {
   __shared__ int h[kBuckets];
   if (threadIdx.x < kBuckets) h[threadIdx.x] = 0;
   __syncthreads();
   int64_t o = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
   if (o < n) {
-    int key = row_key(nbr + o * K, ksize, K);
+    int key = keys_in ? (int)keys_in[o] : row_key(nbr + o * K, ksize, K);
     keys[o] = (uint8_t)key;
     atomicAdd(&h[key], 1);
   }
@@ -155,7 +172,7 @@ extern "C" {
 
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t* nbr,
-                    int32_t* pair_count, void* stream) {
+                    int32_t* pair_count, uint8_t* row_keys, void* stream) {
   GCLB_CHECK_ARG(in_table && (n_out == 0 || (out_coords4 && nbr)), "null pointer");
   GCLB_CHECK_ARG(in_capacity >= 2 && (in_capacity & (in_capacity - 1)) == 0, "bad capacity");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1),
@@ -165,7 +182,8 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   int64_t blocks = (n_out + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
-      make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, nbr, pair_count);
+      make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, nbr, pair_count,
+      row_keys);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
@@ -198,8 +216,8 @@ size_t gclb_kmap_sort_workspace_bytes(int64_t n_out) {
   return (size_t)(((n_out + 15) & ~15ll) + (kBuckets * nb + 8) * 4);
 }
 
-int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_t* perm_out, int32_t* nbr_sorted_out,
-                        uint32_t* tile_mask_out, void* workspace, void* stream) {
+int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys, int32_t* perm_out,
+                        int32_t* nbr_sorted_out, uint32_t* tile_mask_out, void* workspace, void* stream) {
   GCLB_CHECK_ARG(workspace && ksize >= 1 && ksize <= 7, "bad arguments");
   if (n_out == 0) return GCLB_OK;
   GCLB_CHECK_ARG(nbr && perm_out && nbr_sorted_out, "null pointer");
@@ -209,7 +227,7 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_
   const int64_t nb = compact_blocks(n_out);
   uint8_t* keys = (uint8_t*)workspace;
   int32_t* hist = (int32_t*)(keys + ((n_out + 15) & ~15ll));
-  rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, keys, hist, nb);
+  rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, row_keys, keys, hist, nb);
   launch_scan_block_counts(hist, kBuckets * nb, nullptr, st);
   rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out);
   int64_t blocks = (n_out + 7) / 8;

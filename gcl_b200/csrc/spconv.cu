@@ -211,6 +211,62 @@ __global__ void __launch_bounds__(256) spconv_fwd_small_cin_kernel(ConvParams p)
   }
 }
 
+// Same layer with the kernel map FUSED: instead of reading a [n, K] neighbour table the warp probes the coordinate hash
+// itself (32 offsets at a time).  For conv1 (K = 125) this removes the 4*K*n-byte table write + read (163 MB per 325k
+// voxels) and its separate build pass; the probes hit the L2-resident hash table.
+template <int CIN>
+__global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvParams p, HashTable t,
+                                                                          const int32_t* __restrict__ coords4, int ksize,
+                                                                          int step) {
+  extern __shared__ float Ws[];  // [K*CIN][cout]
+  const int K = p.K, cout = p.cout;
+  for (int e = threadIdx.x; e < K * CIN * cout; e += blockDim.x) Ws[e] = __ldg(p.W + e);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int half = (ksize & 1) ? ksize / 2 : 0;
+  for (int64_t o = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); o < p.n_out; o += (int64_t)gridDim.x * wpb) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords4) + o);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};          // output channels lane, lane+32, lane+64, lane+96
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      int idx = -1;
+      if (k < K) {
+        int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
+        int x = c.y + (ix - half) * step, y = c.z + (iy - half) * step, z = c.w + (iz - half) * step;
+        if (coord_in_range(c.x, x, y, z)) idx = hash_find(t, pack_key(c.x, x, y, z));
+      }
+      float f[CIN];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) f[ci] = idx >= 0 ? __ldg(p.in0 + (size_t)idx * CIN + ci) : 0.f;
+      unsigned m = __ballot_sync(0xffffffffu, idx >= 0);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int kk = k0 + src;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float fv = __shfl_sync(0xffffffffu, f[ci], src);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = lane + 32 * q;
+            if (n < cout) acc[q] = fmaf(fv, Ws[(kk * CIN + ci) * cout + n], acc[q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = lane + 32 * q;
+      if (n < cout) {
+        float v = acc[q] * (p.scale ? __ldg(p.scale + n) : 1.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
+        if (p.residual) v += __ldg(p.residual + (size_t)o * cout + n);
+        p.out[(size_t)o * cout + n] = (p.relu & 1) ? fmaxf(v, 0.f) : v;
+      }
+    }
+  }
+}
+
 template <int BM, int BN, bool VEC>
 static cudaError_t launch_f32(const ConvParams& p, cudaStream_t st) {
   size_t smem = (size_t)(BK * (BM + 4) + BK * (BN + 4)) * 4 + (size_t)(BM * p.K + p.K) * 4;
@@ -368,6 +424,37 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
     return GCLB_ERR_CUDA;
   }
   count_launches(1);
+  return GCLB_OK;
+}
+
+int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
+                          int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
+                          const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                          void* stream) {
+  GCLB_CHECK_ARG(W && table && (n == 0 || (in && coords4 && out)), "null pointer");
+  GCLB_CHECK_ARG(cin >= 1 && cin <= 4 && cout >= 1 && cout <= 128, "fused-probe convolution covers cin <= 4, cout <= 128");
+  GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && tensor_stride >= 1 && dilation >= 1, "bad kernel geometry");
+  GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0, "bad capacity");
+  GCLB_CHECK_ARG(relu == 0 || relu == 1, "relu must be 0 or 1");
+  if (n == 0) return GCLB_OK;
+  const int K = ksize * ksize * ksize;
+  const size_t smem = (size_t)K * cin * cout * 4;
+  GCLB_CHECK_ARG(smem <= 200 * 1024, "weights do not fit in shared memory");
+  ConvParams p{in, nullptr, cin, 0, W, K, cout, nullptr, nullptr, nullptr, scale, shift, residual, relu, out, n};
+  HashTable t = make_table(table, capacity);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(p, t, coords4, ksize, tensor_stride * dilation);
+  };
+  if (cin == 1) launch(spconv_fwd_probe_small_cin_kernel<1>);
+  else if (cin == 2) launch(spconv_fwd_probe_small_cin_kernel<2>);
+  else if (cin == 3) launch(spconv_fwd_probe_small_cin_kernel<3>);
+  else launch(spconv_fwd_probe_small_cin_kernel<4>);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
 

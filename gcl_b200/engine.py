@@ -53,6 +53,8 @@ class ResUNetEngine:
     self.tc = {}
     self.tail_tc = None
     self.sort_rows = True
+    # conv1 with a narrow input: fuse the kernel map into the convolution (no 4*K*N-byte table for the 5^3 kernel)
+    self.conv1_probe = (self.p["conv1"][0].shape[1] <= 4 and self.p["conv1"][0].shape[2] <= 128)
     if algo != 1:
       for key, (W, _, _) in self.p.items():
         K, cin, cout = W.shape
@@ -98,17 +100,21 @@ class ResUNetEngine:
     ops.finish_maps([cm1, cm2, cm4, cm8])
     cms = {1: cm1, 2: cm2, 4: cm4, 8: cm8}
     km = {}
-    if self.conv1_ks != 1:
-      km["c1"] = ops.kernel_map(cm1, cm1, self.conv1_ks)
+    sort = bool(self.tc) and self.sort_rows     # row-bucketed copies for the tensor-core kernel
+
+    def table(in_cm, out_cm, ks, transposed=False, tc=True):
+      if sort and tc:
+        t, keys = ops.kernel_map(in_cm, out_cm, ks, transposed=transposed, with_keys=True)
+        return (t,) + ops.kernel_map_sort(t, keys)
+      return ops.kernel_map(in_cm, out_cm, ks, transposed=transposed)
+
+    if self.conv1_ks != 1 and not self.conv1_probe:
+      km["c1"] = table(cm1, cm1, self.conv1_ks, tc=(self.conv1_ks == 3))
     for s in (1, 2, 4, 8):
-      km[f"k3s{s}"] = ops.kernel_map(cms[s], cms[s], 3) if not (s == 1 and self.conv1_ks == 3) else km["c1"]
+      km[f"k3s{s}"] = table(cms[s], cms[s], 3) if not (s == 1 and self.conv1_ks == 3 and "c1" in km) else km["c1"]
     for s in (1, 2, 4):
-      km[f"down{s}"] = ops.kernel_map(cms[s], cms[2 * s], 3)
-      km[f"up{s}"] = ops.kernel_map(cms[2 * s], cms[s], 3, transposed=True)
-    if self.tc and self.sort_rows:       # row-bucketed copies for the tensor-core kernel
-      for name, t in list(km.items()):
-        if name != "c1" or self.conv1_ks == 3:
-          km[name] = (t,) + ops.kernel_map_sort(t)
+      km[f"down{s}"] = table(cms[s], cms[2 * s], 3)
+      km[f"up{s}"] = table(cms[2 * s], cms[s], 3, transposed=True)
     return cms, km
 
   @torch.no_grad()
@@ -118,7 +124,12 @@ class ResUNetEngine:
     self.last_maps = (cms, km)
     n1, n2, n4, n8 = cms[1].n, cms[2].n, cms[4].n, cms[8].n
     x = feats.contiguous().float()
-    s1 = self._block("block1", self._conv("conv1", x, km.get("c1"), n1), km["k3s1"])
+    if self.conv1_probe:
+      W, sc, sh = self.p["conv1"]
+      c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
+    else:
+      c1 = self._conv("conv1", x, km.get("c1"), n1)
+    s1 = self._block("block1", c1, km["k3s1"])
     s2 = self._block("block2", self._conv("conv2", s1, km["down1"], n2), km["k3s2"])
     s4 = self._block("block3", self._conv("conv3", s2, km["down2"], n4), km["k3s4"])
     s8 = self._block("block4", self._conv("conv4", s4, km["down4"], n8), km["k3s8"])

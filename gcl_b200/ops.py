@@ -149,16 +149,19 @@ finish_stride_maps = finish_maps
 
 
 def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1, transposed: bool = False,
-               count_pairs: bool = False):
+               count_pairs: bool = False, with_keys: bool = False):
   """K2 neighbour table nbr int32 [n_out, ksize^3] (see include/gclb200.h).  Forward: offsets scale with the
   input tensor stride; transposed (A7): out map is the finer one and offsets scale with ITS stride, negated."""
   K = ksize ** 3
   dev = out_cm.coords.device
   nbr = torch.empty((out_cm.n, K), dtype=torch.int32, device=dev)
   counts = torch.zeros(K, dtype=torch.int32, device=dev) if count_pairs else None
+  keys = torch.empty(out_cm.n, dtype=torch.uint8, device=dev) if with_keys else None
   step = out_cm.tensor_stride if transposed else in_cm.tensor_stride
   call("gclb_kmap_build", ptr(in_cm.table), in_cm.capacity, ptr(out_cm.coords), out_cm.n, ksize, step, dilation,
-       -1 if transposed else 1, ptr(nbr), ptr(counts), stream())
+       -1 if transposed else 1, ptr(nbr), ptr(counts), ptr(keys), stream())
+  if with_keys:
+    return nbr, keys
   return (nbr, counts) if count_pairs else nbr
 
 
@@ -176,7 +179,7 @@ def kernel_map_pairs(nbr: torch.Tensor):
   return in_idx[:total], out_idx[:total], off
 
 
-def kernel_map_sort(nbr: torch.Tensor):
+def kernel_map_sort(nbr: torch.Tensor, keys: Optional[torch.Tensor] = None):
   """Group table rows by neighbour-direction pattern for the tcgen05 kernel: returns (nbr_sorted, perm, tile_mask) with
   nbr_sorted[t] = nbr[perm[t]] and tile_mask[t // 128] = bit mask of the offsets populated in that 128-row tile."""
   n_out, K = nbr.shape
@@ -187,7 +190,7 @@ def kernel_map_sort(nbr: torch.Tensor):
   out = torch.empty_like(nbr)
   mask = torch.empty((n_out + 127) // 128, dtype=torch.int32, device=nbr.device) if K <= 32 else None
   ws = _workspace(lib.gclb_kmap_sort_workspace_bytes(n_out), nbr.device)
-  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(perm), ptr(out), ptr(mask), ptr(ws), stream())
+  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(keys), ptr(perm), ptr(out), ptr(mask), ptr(ws), stream())
   return out, perm, mask
 
 
@@ -215,6 +218,20 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
        ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)) | (2 if normalize else 0), ptr(out), n_out, algo,
        stream())
+  return out
+
+
+def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int, dilation: int = 1, scale=None,
+                     shift=None, residual=None, relu=False) -> torch.Tensor:
+  """stride-1 convolution of a narrow input (cin <= 4) with the kernel map fused into the kernel (hash probes instead
+  of a neighbour table): conv1 of the ResUNet."""
+  require_cuda(x, W)
+  K, cin, cout = W.shape
+  assert K == ksize ** 3 and x.shape[1] == cin and x.shape[0] == cm.n
+  out = torch.empty((cm.n, cout), dtype=torch.float32, device=x.device)
+  call("gclb_spconv_fwd_probe", ptr(x.contiguous()), cin, ptr(W.contiguous()), ksize, cout, ptr(cm.table), cm.capacity,
+       ptr(cm.coords), cm.n, cm.tensor_stride, dilation, ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
+       ptr(out), stream())
   return out
 
 

@@ -101,10 +101,12 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
  * map, offset_stride = input tensor stride, sign=+1.  Transposed conv (model/resunet.py:101-134): in_table =
  * coarse map, out_coords = fine map, offset_stride = fine tensor stride, sign=-1.
  *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
+ *   row_keys uint8 [n_out] or NULL: 6-bit neighbour-direction key of every row, computed for free during the build
+ *            and accepted by gclb_kmap_sort_rows.
  * ---------------------------------------------------------------------------------------------------- */
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t* nbr,
-                    int32_t* pair_count, void* stream);
+                    int32_t* pair_count, uint8_t* row_keys, void* stream);
 /* expand a neighbour table into ME-style per-offset pair lists, canonical order (k ascending, out row
  * ascending): in_idx/out_idx int32 [n_out*K] (first offset_ptr[K] valid), offset_ptr int64 [K+1]. */
 int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_idx, int32_t* out_idx,
@@ -115,8 +117,9 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
  * [ceil(n_out/128)] or NULL (ksize^3 <= 32): bit k set iff offset k is populated in that 128-row tile.  Pure re-ordering: pass
  * both to gclb_spconv_fwd(algo=2); results are identical, the kernel just runs ~2-8x fewer pipeline stages. */
 size_t gclb_kmap_sort_workspace_bytes(int64_t n_out);
-int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, int32_t* perm_out, int32_t* nbr_sorted_out,
-                        uint32_t* tile_mask_out, void* workspace, void* stream);
+int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys /* or NULL */,
+                        int32_t* perm_out, int32_t* nbr_sorted_out, uint32_t* tile_mask_out, void* workspace,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K3 sparse convolution forward, output-stationary implicit GEMM with fused epilogue
@@ -146,6 +149,13 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
                     const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
                     int64_t n_out, int32_t algo, void* stream);
+/* stride-1 convolution with a small input width (cin <= 4, e.g. conv1 of ResUNet: cin = 1, kernel 5^3) with the kernel
+ * map FUSED into the convolution: the kernel probes the coordinate hash of the (single) coordinate map itself, so no
+ * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd. */
+int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
+                          int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
+                          const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                          void* stream);
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
                       const int32_t* nbr, int32_t K, float* gW, void* stream);

@@ -296,6 +296,20 @@ def test_spconv_two_source_and_pointwise(G):
   assert _rel(got_mm, a @ W1[:64]) < FP32_TOL
 
 
+@pytest.mark.parametrize("cin,cout,ks", [(1, 32, 5), (3, 16, 3), (4, 64, 3)])
+def test_spconv_probe_fused_kernel_map(G, cin, cout, ks):
+  torch.manual_seed(31)
+  C_ref, _ = _oracle_voxelize([_random_cloud(27, 3000, 8.0), _random_cloud(28, 2000, 6.0)], 0.3)
+  n = len(C_ref)
+  nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(ks, 1))
+  x, W = torch.randn(n, cin), torch.randn(ks ** 3, cin, cout) / np.sqrt(cin * ks ** 3)
+  sc, sh = torch.rand(cout) + 0.5, torch.randn(cout)
+  ref = OME.sparse_conv_reference(x, W, nbr, n) * sc + sh
+  cm = G.ops.hash_build(C_ref.to(G.dev))
+  got = G.ops.spconv_fwd_probe(x.to(G.dev), W.to(G.dev), cm, ks, scale=sc.to(G.dev), shift=sh.to(G.dev))
+  assert _rel(got, ref) < FP32_TOL
+
+
 def _seed_bn(model):
   g = torch.Generator().manual_seed(123)
   for m in model.modules():
