@@ -49,7 +49,7 @@ int gclb_has_tcgen05(void);
  * Replaces ME's CoordinateMapGPU insert/find (SparseTensor construction: scripts/test_kitti.py:143-148,
  * lib/colocation_trainer.py:843-845, util/misc.py:128).
  * ---------------------------------------------------------------------------------------------------- */
-int64_t gclb_hash_capacity(int64_t n_rows);           /* power of two >= 2*n_rows, >= 1024 */
+int64_t gclb_hash_capacity(int64_t n_rows);           /* power of two >= 4*n_rows, >= 1024 */
 size_t gclb_hash_bytes(int64_t capacity);
 /* insert N unique rows; vals = row index.  Duplicates keep the smallest row index and set GCLB_ST_DUPLICATE. */
 int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64_t n, int32_t* status, void* stream);
