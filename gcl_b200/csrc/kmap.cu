@@ -7,8 +7,8 @@ namespace gclb {
 
 __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int32_t* __restrict__ out_c4,
                                                          int64_t n_out, int ksize, int K, int step, int sign,
-                                                         int32_t* __restrict__ nbr, int32_t* __restrict__ pair_count,
-                                                         uint8_t* __restrict__ row_keys) {
+                                                         int in_stride, int32_t* __restrict__ nbr,
+                                                         int32_t* __restrict__ pair_count, uint8_t* __restrict__ row_keys) {
   extern __shared__ int s_count[];  // [K]
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_count[k] = 0;
   __syncthreads();
@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
         int x = c.y + sign * (ix - half) * step;
         int y = c.z + sign * (iy - half) * step;
         int z = c.w + sign * (iz - half) * step;
-        r = coord_in_range(c.x, x, y, z) ? hash_find(t, pack_key(c.x, x, y, z)) : -1;
+        // rows of the probed map sit on multiples of ITS tensor stride: a misaligned candidate (19 of the 27 offsets of
+        // every fine voxel of a transposed map) cannot exist and is rejected without touching the table
+        const bool aligned = in_stride <= 1 || ((x % in_stride) == 0 && (y % in_stride) == 0 && (z % in_stride) == 0);
+        r = (aligned && coord_in_range(c.x, x, y, z)) ? hash_find(t, pack_key(c.x, x, y, z)) : -1;
         nbr[o * K + k] = r;
         if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
       }
@@ -145,21 +148,33 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uin
   }
 }
 
+// one thread per table ENTRY: coalesced writes, reads in 4*K-byte runs; tile masks through a warp-level OR when the whole
+// warp sits in one 128-row tile (the common case: a warp spans ~1.2 rows)
+template <int KC>   // KC = K when known at compile time (27), 0 = runtime K
 __global__ void __launch_bounds__(256) permute_rows_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ perm,
-                                                           int64_t n, int K, int32_t* __restrict__ out,
+                                                           int64_t n, int K_rt, int32_t* __restrict__ out,
                                                            uint32_t* __restrict__ tile_mask) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int64_t t = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * wpb) {
-    const int64_t o = perm[t];
-    for (int k0 = 0; k0 < K; k0 += 32) {
-      const int k = k0 + lane;
-      int v = -1;
-      if (k < K) { v = __ldg(&nbr[o * K + k]); out[t * K + k] = v; }
-      if (tile_mask && k0 == 0) {      // K <= 32: which offsets are populated anywhere in the 128-row tile
-        unsigned m = __ballot_sync(0xffffffffu, v >= 0);
-        if (lane == 0 && m) atomicOr(&tile_mask[t >> 7], m);
-      }
+  const int K = KC ? KC : K_rt;
+  const int64_t total = n * K;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = e < total;
+  int64_t t = 0;
+  int k = 0, v = -1;
+  if (in) {
+    t = e / K;
+    k = (int)(e - t * K);
+    v = __ldg(&nbr[(int64_t)__ldg(&perm[t]) * K + k]);
+    out[e] = v;
+  }
+  if (tile_mask) {
+    const int64_t tile = in ? (t >> 7) : -1;
+    const unsigned bit = (in && v >= 0) ? (1u << k) : 0u;
+    const int64_t tile0 = __shfl_sync(0xffffffffu, tile, 0);
+    if (__all_sync(0xffffffffu, tile == tile0)) {
+      const unsigned m = __reduce_or_sync(0xffffffffu, bit);
+      if ((threadIdx.x & 31) == 0 && m && tile0 >= 0) atomicOr(&tile_mask[tile0], m);
+    } else if (bit) {
+      atomicOr(&tile_mask[tile], bit);
     }
   }
 }
@@ -171,19 +186,20 @@ using namespace gclb;
 extern "C" {
 
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
-                    int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t* nbr,
-                    int32_t* pair_count, uint8_t* row_keys, void* stream) {
+                    int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, void* stream) {
   GCLB_CHECK_ARG(in_table && (n_out == 0 || (out_coords4 && nbr)), "null pointer");
   GCLB_CHECK_ARG(in_capacity >= 2 && (in_capacity & (in_capacity - 1)) == 0, "bad capacity");
-  GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1),
+  GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1) &&
+                     in_tensor_stride >= 0,
                  "bad kernel geometry");
   if (n_out == 0) return GCLB_OK;
   int K = ksize * ksize * ksize;
   int64_t blocks = (n_out + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
-      make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, nbr, pair_count,
-      row_keys);
+      make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, in_tensor_stride,
+      nbr, pair_count, row_keys);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
@@ -230,13 +246,14 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
   rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, row_keys, keys, hist, nb);
   launch_scan_block_counts(hist, kBuckets * nb, nullptr, st);
   rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out);
-  int64_t blocks = (n_out + 7) / 8;
-  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  const int64_t blocks = (n_out * K + 255) / 256;
+  GCLB_CHECK_ARG(blocks < (1ll << 31), "kernel map too large");
   if (tile_mask_out) {
     GCLB_CHECK_ARG(K <= 32, "tile masks need ksize^3 <= 32");
     cudaMemsetAsync(tile_mask_out, 0, (size_t)((n_out + 127) / 128) * 4, st);
   }
-  permute_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
+  if (K == 27) permute_rows_kernel<27><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
+  else permute_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
   count_launches(4);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

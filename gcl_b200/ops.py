@@ -19,9 +19,11 @@ class CoordMap:
     self.status = status      # device int32 status word still to be checked (maps built with sync=False)
 
 
-def _new_table(n_rows: int, device) -> Tuple[torch.Tensor, int]:
+def _new_table(n_rows: int, device, upper_bound: bool = False) -> Tuple[torch.Tensor, int]:
+  """upper_bound: n_rows is a host-side bound (point count / parent rows) far above the rows that will be inserted, so
+  half the usual slack already gives a very low load factor (and halves the memset)."""
   lib = _lib.load()
-  cap = int(lib.gclb_hash_capacity(int(n_rows)))
+  cap = int(lib.gclb_hash_capacity(int(n_rows + 1) // 2 if upper_bound else int(n_rows)))
   return torch.empty(int(lib.gclb_hash_bytes(cap)), dtype=torch.uint8, device=device), cap
 
 
@@ -66,7 +68,7 @@ def voxelize(xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] 
   n_clouds = cloud_ptr.numel() - 1
   cloud_ptr = cloud_ptr.to(device=dev, dtype=torch.int64).contiguous()
   lib = _lib.load()
-  table, cap = _new_table(P, dev)
+  table, cap = _new_table(P, dev, upper_bound=True)
   coords = torch.empty((P, 4), dtype=torch.int32, device=dev)
   umap = torch.empty(P, dtype=torch.int64, device=dev)
   inv = torch.empty(P, dtype=torch.int32, device=dev) if return_inverse else None
@@ -115,7 +117,7 @@ def stride_map(cm: CoordMap, stride: int, return_parent_rows=False, sync: bool =
   lib = _lib.load()
   n_in_dev = cm.n if isinstance(cm.n, torch.Tensor) else None     # parent not finished yet: chain on the device
   n_in = cm.coords.shape[0] if n_in_dev is not None else cm.n     # host-side upper bound
-  table, cap = _new_table(n_in, dev)
+  table, cap = _new_table(n_in, dev, upper_bound=True)
   coords = torch.empty((n_in, 4), dtype=torch.int32, device=dev)
   parent = torch.empty(n_in, dtype=torch.int32, device=dev) if return_parent_rows else None
   n_out = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -159,7 +161,7 @@ def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1,
   keys = torch.empty(out_cm.n, dtype=torch.uint8, device=dev) if with_keys else None
   step = out_cm.tensor_stride if transposed else in_cm.tensor_stride
   call("gclb_kmap_build", ptr(in_cm.table), in_cm.capacity, ptr(out_cm.coords), out_cm.n, ksize, step, dilation,
-       -1 if transposed else 1, ptr(nbr), ptr(counts), ptr(keys), stream())
+       -1 if transposed else 1, in_cm.tensor_stride, ptr(nbr), ptr(counts), ptr(keys), stream())
   if with_keys:
     return nbr, keys
   return (nbr, counts) if count_pairs else nbr

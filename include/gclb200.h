@@ -100,13 +100,15 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
  * Forward conv (model/resunet.py:38-95, residual_block.py:23-33): in_table = input map, out_coords = output
  * map, offset_stride = input tensor stride, sign=+1.  Transposed conv (model/resunet.py:101-134): in_table =
  * coarse map, out_coords = fine map, offset_stride = fine tensor stride, sign=-1.
+ *   in_tensor_stride: tensor stride of the probed (input) map, or 0/1 if unknown: candidates not aligned to it are
+ *            rejected without a table access (most offsets of a transposed map).
  *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
  *   row_keys uint8 [n_out] or NULL: 6-bit neighbour-direction key of every row, computed for free during the build
  *            and accepted by gclb_kmap_sort_rows.
  * ---------------------------------------------------------------------------------------------------- */
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
-                    int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t* nbr,
-                    int32_t* pair_count, uint8_t* row_keys, void* stream);
+                    int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, void* stream);
 /* expand a neighbour table into ME-style per-offset pair lists, canonical order (k ascending, out row
  * ascending): in_idx/out_idx int32 [n_out*K] (first offset_ptr[K] valid), offset_ptr int64 [K+1]. */
 int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_idx, int32_t* out_idx,
