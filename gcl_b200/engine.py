@@ -24,6 +24,33 @@ def _fold(conv, norm, device):
   return W, scale.to(device).float().contiguous(), shift.to(device).float().contiguous()
 
 
+class _Tables:
+  """name -> kernel map (table or (table, sorted table, perm, tile masks)); a table built on a side stream carries an
+  event that the consuming stream waits on at its first use."""
+
+  def __init__(self):
+    self._t, self._ev = {}, {}
+
+  def put(self, name, t, ev):
+    self._t[name], self._ev[name] = t, ev
+
+  def alias(self, name, other):
+    self._t[name], self._ev[name] = self._t[other], self._ev.get(other)
+
+  def __contains__(self, name):
+    return name in self._t
+
+  def __getitem__(self, name):
+    ev = self._ev.get(name)
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
+      self._ev[name] = None
+    return self._t[name]
+
+  def items(self):
+    return [(k, self[k]) for k in self._t]
+
+
 class ResUNetEngine:
   """Build from any ResUNet2-family module (reference class or gcl_b200.resunet) holding the trained weights."""
 
@@ -53,6 +80,7 @@ class ResUNetEngine:
     self.tc = {}
     self.tail_tc = None
     self.sort_rows = True
+    self._side = None      # side streams for overlapped kernel-map construction
     # conv1 with a narrow input: fuse the kernel map into the convolution (no 4*K*N-byte table for the 5^3 kernel)
     self.conv1_probe = (self.p["conv1"][0].shape[1] <= 4 and self.p["conv1"][0].shape[2] <= 128)
     if algo != 1:
@@ -90,16 +118,24 @@ class ResUNetEngine:
     t = self._conv(name + ".1", x, nbr, n, relu=True)
     return self._conv(name + ".2", t, nbr, n, residual=x, relu=True)
 
-  def build_maps(self, cm1: ops.CoordMap):
-    """strided maps + all kernel maps of one forward (cacheable by the caller for repeated forwards).  The three
-    strided levels are chained on the device and finished -- together with cm1 if it came from voxelize(sync=False) --
-    by ONE host read of the row counts."""
+  # order in which forward() first touches each table
+  TABLE_ORDER = ("c1", "k3s1", "down1", "k3s2", "down2", "k3s4", "down4", "k3s8", "up4", "up2", "up1")
+
+  def build_maps(self, cm1: ops.CoordMap, overlap: bool = False):
+    """strided maps + all kernel maps of one forward (cacheable by the caller for repeated forwards).
+
+    * The three strided levels are chained on the device and finished -- together with cm1 if it came from
+      voxelize(sync=False) -- by ONE host read of the row counts.
+    * The 10-11 kernel maps are independent chains of small, latency-bound kernels (probe, key histogram, scan, scatter,
+      permute).  With `overlap` they are enqueued round-robin on side streams in the order forward() needs them, so they
+      overlap each other and the first convolutions; forward() waits on a table's event right before its first use.
+      Measured on B200 (round 1): SLOWER (7.0 vs 4.5 ms per 8-pair step) -- cross-stream allocator traffic and the
+      persistent 200 KB-smem conv CTAs leave no room for co-residency -- so it is off by default."""
     cm2 = ops.stride_map(cm1, 2, sync=False)
     cm4 = ops.stride_map(cm2, 2, sync=False)
     cm8 = ops.stride_map(cm4, 2, sync=False)
     ops.finish_maps([cm1, cm2, cm4, cm8])
     cms = {1: cm1, 2: cm2, 4: cm4, 8: cm8}
-    km = {}
     sort = bool(self.tc) and self.sort_rows     # row-bucketed copies for the tensor-core kernel
 
     def table(in_cm, out_cm, ks, transposed=False, tc=True):
@@ -108,13 +144,43 @@ class ResUNetEngine:
         return (t,) + ops.kernel_map_sort(t, keys)
       return ops.kernel_map(in_cm, out_cm, ks, transposed=transposed)
 
+    recipes = {}
     if self.conv1_ks != 1 and not self.conv1_probe:
-      km["c1"] = table(cm1, cm1, self.conv1_ks, tc=(self.conv1_ks == 3))
+      recipes["c1"] = lambda: table(cm1, cm1, self.conv1_ks, tc=(self.conv1_ks == 3))
     for s in (1, 2, 4, 8):
-      km[f"k3s{s}"] = table(cms[s], cms[s], 3) if not (s == 1 and self.conv1_ks == 3 and "c1" in km) else km["c1"]
+      if not (s == 1 and self.conv1_ks == 3 and "c1" in recipes):
+        recipes[f"k3s{s}"] = (lambda s=s: table(cms[s], cms[s], 3))
     for s in (1, 2, 4):
-      km[f"down{s}"] = table(cms[s], cms[2 * s], 3)
-      km[f"up{s}"] = table(cms[2 * s], cms[s], 3, transposed=True)
+      recipes[f"down{s}"] = (lambda s=s: table(cms[s], cms[2 * s], 3))
+      recipes[f"up{s}"] = (lambda s=s: table(cms[2 * s], cms[s], 3, transposed=True))
+
+    km = _Tables()
+    main = torch.cuda.current_stream()
+    if not overlap:
+      for name in self.TABLE_ORDER:
+        if name in recipes:
+          km.put(name, recipes[name](), None)
+    else:
+      if self._side is None:
+        self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+      for s_ in self._side:
+        s_.wait_stream(main)                      # coordinate maps are ready
+      i = 0
+      for name in self.TABLE_ORDER:
+        if name not in recipes:
+          continue
+        st = self._side[i % len(self._side)]
+        i += 1
+        with torch.cuda.stream(st):
+          t = recipes[name]()
+          ev = torch.cuda.Event()
+          ev.record(st)
+        for x in (t if isinstance(t, tuple) else (t,)):
+          if x is not None:
+            x.record_stream(main)                 # consumed on the main stream: keep the allocator from recycling early
+        km.put(name, t, ev)
+    if "k3s1" not in recipes and "c1" in recipes:
+      km.alias("k3s1", "c1")
     return cms, km
 
   @torch.no_grad()
@@ -128,7 +194,7 @@ class ResUNetEngine:
       W, sc, sh = self.p["conv1"]
       c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
     else:
-      c1 = self._conv("conv1", x, km.get("c1"), n1)
+      c1 = self._conv("conv1", x, km["c1"] if self.conv1_ks != 1 else None, n1)
     s1 = self._block("block1", c1, km["k3s1"])
     s2 = self._block("block2", self._conv("conv2", s1, km["down1"], n2), km["k3s2"])
     s4 = self._block("block3", self._conv("conv3", s2, km["down2"], n4), km["k3s4"])
