@@ -54,6 +54,7 @@ class CoordinateManager:
     self.D = D
     self.maps: Dict[CoordinateMapKey, ops.CoordMap] = {}
     self.kmaps: Dict[tuple, torch.Tensor] = {}
+    self.kmaps_sorted: Dict[tuple, tuple] = {}
     self.stats = {"kmap_builds": 0, "stride_builds": 0}
 
   def insert(self, coords4: torch.Tensor, tensor_stride=(1, 1, 1)) -> CoordinateMapKey:
@@ -89,6 +90,13 @@ class CoordinateManager:
       self.kmaps[ck] = ops.kernel_map(self.maps[in_key], self.maps[out_key], kernel_size, dilation, transposed)
       self.stats["kmap_builds"] += 1
     return self.kmaps[ck]
+
+  def kernel_map_sorted(self, in_key, out_key, kernel_size: int, dilation: int, transposed: bool):
+    """row-bucketed copy (sorted table, perm, tile masks) of a cached kernel map for the tcgen05 kernel"""
+    ck = (in_key, out_key, kernel_size, dilation, transposed)
+    if ck not in self.kmaps_sorted:
+      self.kmaps_sorted[ck] = ops.kernel_map_sort(self.kernel_map(in_key, out_key, kernel_size, dilation, transposed))
+    return self.kmaps_sorted[ck]
 
   def kernel_map_pairs(self, in_key, out_key, kernel_size, dilation=1, transposed=False):
     """ME-style kernel map {k: (in_idx, out_idx)} in canonical order (debug / parity API)."""
@@ -202,6 +210,18 @@ def cat(*tensors):
   return tensors[0]._like(torch.cat([t.F for t in tensors], dim=1))
 
 
+# Which convolution kernel the module path uses.  Training (autograd active) always runs the exact-fp32 kernels so that
+# gradients match the reference's fp32 arithmetic; inference uses the tcgen05 kind::tf32 kernel where it applies.
+_CONV_ALGO = {"inference": "auto"}
+
+
+def set_inference_conv_algo(name: str):
+  """'auto' (tcgen05 kind::tf32 where supported, else fp32) or 'fp32' (exact-fp32 CUDA-core kernels everywhere)."""
+  if name not in ("auto", "fp32"):
+    raise ValueError("algo must be 'auto' or 'fp32'")
+  _CONV_ALGO["inference"] = name
+
+
 class MinkowskiNetwork(nn.Module):
   def __init__(self, D):
     super().__init__()
@@ -251,6 +271,7 @@ class _ConvBase(nn.Module):
     shape = (in_channels, out_channels) if self.use_mm else (self.kernel_volume, in_channels, out_channels)
     self.kernel = nn.Parameter(torch.empty(shape))
     self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+    self._tc_cache = None
     self.reset_parameters()
 
   def reset_parameters(self):
@@ -295,7 +316,19 @@ class _ConvBase(nn.Module):
         out = out + self.bias
     else:
       shift = self.bias.detach().reshape(-1) if self.bias is not None else None
-      out = ops.spconv_fwd(x.F.detach().contiguous(), self.kernel.detach(), nbr_f, n_out, shift=shift)
+      xf = x.F.detach().contiguous()
+      if _CONV_ALGO["inference"] != "fp32" and ops.tc_supported(self.in_channels, 0, self.out_channels, self.kernel_volume):
+        # inference: tcgen05 kind::tf32 kernel (features within 1e-3 of fp32); weight image cached per parameter version
+        ver = (self.kernel._version, self.kernel.data_ptr())
+        if self._tc_cache is None or self._tc_cache[0] != ver:
+          self._tc_cache = (ver, ops.weights_to_tc(self.kernel.detach()))
+        if self.use_mm:
+          out = ops.spconv_fwd(xf, self._tc_cache[1], None, n_out, shift=shift, algo=2)
+        else:
+          srt, perm, mask = mgr.kernel_map_sorted(in_key, out_key, self.kernel_size, self.dilation, self.TRANSPOSED)
+          out = ops.spconv_fwd(xf, self._tc_cache[1], srt, n_out, shift=shift, algo=2, row_perm=perm, tile_mask=mask)
+      else:
+        out = ops.spconv_fwd(xf, self.kernel.detach(), nbr_f, n_out, shift=shift)
     return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
 
   def extra_repr(self):

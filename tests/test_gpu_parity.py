@@ -347,6 +347,15 @@ def test_resunet_module_path_vs_oracle(G, net):
   assert out.coordinate_map_key == st.coordinate_map_key
   assert st.coordinate_manager.stats == {"kmap_builds": 11, "stride_builds": 3}
   assert _rel(out.F, ref) < FEAT_TOL
+  # the same modules with the exact-fp32 kernels everywhere
+  G.ME.set_inference_conv_algo("fp32")
+  try:
+    with torch.no_grad():
+      out32 = gm(G.ME.SparseTensor(F_in.to(G.dev), coordinates=C_ref.to(G.dev)))
+  finally:
+    G.ME.set_inference_conv_algo("auto")
+  assert _rel(out32.F, ref) < 1e-5
+  assert not torch.equal(out32.F, out.F)      # i.e. the default really went through the tensor-core kernels
 
 
 def test_resunet_engine_vs_oracle(G, net):
