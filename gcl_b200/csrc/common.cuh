@@ -66,27 +66,37 @@ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 fmix64
   return (uint32_t)k;
 }
 
+// One 16-byte slot = { uint64 key, uint32 value (row index), uint32 pad }: a probe is ONE 128-bit load (key and value
+// arrive together: no dependent second load on a hit), and the whole table is initialised by a single memset(0xFF)
+// (empty key = ~0, value = UINT_MAX so that atomicMin(row) works on it).
+struct __align__(16) HashSlot {
+  unsigned long long key;
+  unsigned int val;
+  unsigned int pad;
+};
 struct HashTable {
-  unsigned long long* keys;
-  int32_t* vals;
+  HashSlot* slots;
   uint32_t mask;  // capacity - 1
 };
+constexpr unsigned int kValEmpty = 0xffffffffu;
 __host__ __device__ __forceinline__ HashTable make_table(const void* buf, int64_t capacity) {
   HashTable t;
-  t.keys = (unsigned long long*)buf;
-  t.vals = (int32_t*)((char*)buf + (size_t)capacity * 8);
+  t.slots = (HashSlot*)buf;
   t.mask = (uint32_t)(capacity - 1);
   return t;
 }
+__device__ __forceinline__ int table_val(const HashTable& t, int slot) { return (int)t.slots[slot].val; }
 
-// insert key, value = min(existing, row).  Returns slot, or -1 when the table is full.
-__device__ __forceinline__ int hash_insert_min(const HashTable& t, uint64_t key, int row) {
+// insert key, value = min(existing, row).  Returns slot, or -1 when the table is full.  *old_val (optional) receives the
+// previous value (kValEmpty when the slot was fresh).
+__device__ __forceinline__ int hash_insert_min(const HashTable& t, uint64_t key, int row, unsigned int* old_val = nullptr) {
   uint32_t slot = hash_key(key) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; ++probe) {
-    unsigned long long prev = t.keys[slot];
-    if (prev == kEmptyKey) prev = atomicCAS(&t.keys[slot], kEmptyKey, (unsigned long long)key);
+    unsigned long long prev = t.slots[slot].key;
+    if (prev == kEmptyKey) prev = atomicCAS(&t.slots[slot].key, kEmptyKey, (unsigned long long)key);
     if (prev == kEmptyKey || prev == key) {
-      atomicMin(&t.vals[slot], row);
+      unsigned int o = atomicMin(&t.slots[slot].val, (unsigned int)row);
+      if (old_val) *old_val = o;
       return (int)slot;
     }
     slot = (slot + 1) & t.mask;
@@ -96,8 +106,9 @@ __device__ __forceinline__ int hash_insert_min(const HashTable& t, uint64_t key,
 __device__ __forceinline__ int hash_find(const HashTable& t, uint64_t key) {
   uint32_t slot = hash_key(key) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; ++probe) {
-    unsigned long long k = __ldg(&t.keys[slot]);
-    if (k == key) return __ldg(&t.vals[slot]);
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(t.slots + slot));   // one 128-bit load: key + value
+    const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
+    if (k == key) return (int)s.z;
     if (k == kEmptyKey) return -1;
     slot = (slot + 1) & t.mask;
   }

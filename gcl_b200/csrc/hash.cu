@@ -18,7 +18,6 @@ void set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
-constexpr int kValInit = 0x7f7f7f7f;
 
 // ------------------------------------------------------------------------------------------------------------
 // row sources: each yields the (b,x,y,z) a row is keyed on
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(256) insert_rows_kernel(Src src, int64_t n, co
 
 __device__ __forceinline__ bool is_winner(const HashTable& t, const int32_t* slot_of, int64_t i) {
   int s = slot_of[i];
-  return s >= 0 && t.vals[s] == (int)i;
+  return s >= 0 && table_val(t, s) == (int)i;
 }
 
 __global__ void __launch_bounds__(kCompactBlock) count_winners_kernel(int64_t n, const int64_t* n_dev, HashTable t,
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(kCompactBlock) scatter_winners_kernel(Src src,
     if (unique_map_out) unique_map_out[pos] = i;
     // the table now maps coordinate -> compacted row.  Safe against concurrent is_winner() of duplicates:
     // pos <= i < (any losing row index), so a loser can never read its own index here.
-    t.vals[slot_of[i]] = pos;
+    t.slots[slot_of[i]].val = (unsigned int)pos;
   }
 }
 
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(256) inverse_map_kernel(int64_t n, const int64
   if (n_dev) n = min(n, __ldg(n_dev));
   if (i >= n) return;
   int s = slot_of[i];
-  inverse[i] = s >= 0 ? t.vals[s] : -1;
+  inverse[i] = s >= 0 ? table_val(t, s) : -1;
 }
 
 template <class Src>
@@ -166,8 +165,7 @@ static int dedupe_rows(Src src, int64_t n, const int64_t* n_dev, void* table, in
     return GCLB_ERR_ARG;
   }
   HashTable t = make_table(table, capacity);
-  cudaMemsetAsync(t.keys, 0xff, (size_t)capacity * 8, st);
-  cudaMemsetAsync(t.vals, 0x7f, (size_t)capacity * 4, st);
+  cudaMemsetAsync(t.slots, 0xff, (size_t)capacity * sizeof(HashSlot), st);
   if (n == 0) {
     cudaMemsetAsync(n_out, 0, 8, st);
     GCLB_CHECK_LAUNCH();
@@ -192,19 +190,10 @@ __global__ void __launch_bounds__(256) hash_build_kernel(const int32_t* c4, int6
   if (i >= n) return;
   int4 c = __ldg(reinterpret_cast<const int4*>(c4) + i);
   if (!coord_in_range(c.x, c.y, c.z, c.w)) { atomicOr(status, GCLB_ST_RANGE); return; }
-  uint64_t key = pack_key(c.x, c.y, c.z, c.w);
-  uint32_t slot = hash_key(key) & t.mask;
-  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
-    unsigned long long prev = t.keys[slot];
-    if (prev == kEmptyKey) prev = atomicCAS(&t.keys[slot], kEmptyKey, (unsigned long long)key);
-    if (prev == kEmptyKey || prev == key) {
-      int old = atomicMin(&t.vals[slot], (int)i);
-      if (old != kValInit) atomicOr(status, GCLB_ST_DUPLICATE);
-      return;
-    }
-    slot = (slot + 1) & t.mask;
-  }
-  atomicOr(status, GCLB_ST_FULL);
+  unsigned int old = kValEmpty;
+  int slot = hash_insert_min(t, pack_key(c.x, c.y, c.z, c.w), (int)i, &old);
+  if (slot < 0) atomicOr(status, GCLB_ST_FULL);
+  else if (old != kValEmpty) atomicOr(status, GCLB_ST_DUPLICATE);
 }
 
 __global__ void __launch_bounds__(256) hash_query_kernel(HashTable t, const int32_t* q4, int64_t nq, int32_t* rows) {
@@ -232,7 +221,7 @@ int64_t gclb_hash_capacity(int64_t n_rows) {
   while (c < 4 * n_rows) c <<= 1;
   return c;
 }
-size_t gclb_hash_bytes(int64_t capacity) { return (size_t)capacity * 12; }
+size_t gclb_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot); }
 
 size_t gclb_compact_workspace_bytes(int64_t n) {
   return (size_t)(((n + 3) & ~3ll) + compact_blocks(n) + 8) * 4;
@@ -243,8 +232,7 @@ int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity >= n, "bad capacity");
   cudaStream_t st = (cudaStream_t)stream;
   HashTable t = make_table(table, capacity);
-  cudaMemsetAsync(t.keys, 0xff, (size_t)capacity * 8, st);
-  cudaMemsetAsync(t.vals, 0x7f, (size_t)capacity * 4, st);
+  cudaMemsetAsync(t.slots, 0xff, (size_t)capacity * sizeof(HashSlot), st);
   if (n > 0) { hash_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(coords4, n, t, status); count_launches(1); }
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -15,9 +15,12 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int half = (ksize & 1) ? ksize / 2 : 0;
-  for (int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); o < n_out;
-       o += (int64_t)gridDim.x * warps_per_block) {
-    int4 c = __ldg(reinterpret_cast<const int4*>(out_c4) + o);
+  const int64_t o0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int64_t ostep = (int64_t)gridDim.x * warps_per_block;
+  int4 c_next = o0 < n_out ? __ldg(reinterpret_cast<const int4*>(out_c4) + o0) : make_int4(0, 0, 0, 0);
+  for (int64_t o = o0; o < n_out; o += ostep) {
+    const int4 c = c_next;                       // software pipeline: the next row's coordinates are already in flight
+    if (o + ostep < n_out) c_next = __ldg(reinterpret_cast<const int4*>(out_c4) + o + ostep);
     int key = 0;
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;

@@ -66,7 +66,9 @@ def voxelize(xyz: torch.Tensor, voxel: float, cloud_ptr: Optional[torch.Tensor] 
   if cloud_ptr is None:
     cloud_ptr = torch.tensor([0, P], dtype=torch.int64)
   n_clouds = cloud_ptr.numel() - 1
-  cloud_ptr = cloud_ptr.to(device=dev, dtype=torch.int64).contiguous()
+  if not cloud_ptr.is_cuda:   # tiny host array: stage through pinned memory so the copy never blocks the host
+    cloud_ptr = cloud_ptr.to(torch.int64).pin_memory().to(dev, non_blocking=True)
+  cloud_ptr = cloud_ptr.to(dtype=torch.int64).contiguous()
   lib = _lib.load()
   table, cap = _new_table(P, dev, upper_bound=True)
   coords = torch.empty((P, 4), dtype=torch.int32, device=dev)

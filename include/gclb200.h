@@ -44,8 +44,9 @@ int64_t gclb_kernel_launches(void);
 int gclb_has_tcgen05(void);
 
 /* ------------------------------------------------------------------------------------------------------
- * Coordinate hash table: open addressing, linear probing, 64-bit packed keys, int32 values (row index).
- * Layout in the caller's buffer: uint64 keys[capacity] ; int32 vals[capacity].
+ * Coordinate hash table: open addressing, linear probing, 64-bit packed keys, 32-bit values (row index).
+ * Layout in the caller's buffer: capacity 16-byte slots { uint64 key; uint32 value; uint32 pad } (16-byte aligned), so
+ * a probe is one 128-bit load.
  * Replaces ME's CoordinateMapGPU insert/find (SparseTensor construction: scripts/test_kitti.py:143-148,
  * lib/colocation_trainer.py:843-845, util/misc.py:128).
  * ---------------------------------------------------------------------------------------------------- */

@@ -40,7 +40,7 @@ def test_host_side_helpers(lib):
   assert lib.gclb_hash_capacity(0) == 1024
   assert lib.gclb_hash_capacity(1000) == 4096
   assert lib.gclb_hash_capacity(130000) == 524288
-  assert lib.gclb_hash_bytes(1024) == 1024 * 12
+  assert lib.gclb_hash_bytes(1024) == 1024 * 16
   assert lib.gclb_compact_workspace_bytes(5000) >= 5000 * 4
   assert lib.gclb_nn_workspace_bytes(100, 200, 1, 100, 200) >= 300 * 8
 
