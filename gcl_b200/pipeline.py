@@ -18,6 +18,7 @@ class PairMatcher:
     self.voxel, self.subsample = float(voxel), int(subsample)
     self.device = torch.device(device)
     self.seed, self.calls = int(seed) * 1000003, 0
+    self._streams = None
 
   @torch.no_grad()
   def match(self, xyz: torch.Tensor, cloud_ptr: torch.Tensor):
@@ -41,3 +42,28 @@ class PairMatcher:
     pairs, pair_ptr = ops.mutual_filter(idx01, idx10, a_dev, b_dev, ws)
     return dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel[0], sel1=sel[1], a_ptr=a_dev, b_ptr=b_dev, idx01=idx01,
                 idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords)
+
+  def match_many(self, batches, depth: int = 2):
+    """Throughput API: iterate over `(xyz, cloud_ptr)` batches and yield `match()` results in order, keeping `depth`
+    batches in flight on alternating CUDA streams.  A batch has one host synchronisation (the voxel / strided-map row
+    counts); with two streams that bubble -- and the launch gaps of the many small map-building kernels -- are filled by
+    the other batch's convolutions.  Each result is complete (its stream synchronised) when it is yielded."""
+    if self._streams is None or len(self._streams) < depth:
+      self._streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+    cur = torch.cuda.current_stream()
+    pending = []
+    for i, (xyz, cloud_ptr) in enumerate(batches):
+      st = self._streams[i % depth]
+      st.wait_stream(cur)
+      with torch.cuda.stream(st):
+        out = self.match(xyz, cloud_ptr)
+        ev = torch.cuda.Event()
+        ev.record(st)
+      pending.append((out, ev))
+      if len(pending) >= depth:
+        o, e = pending.pop(0)
+        e.synchronize()
+        yield o
+    for o, e in pending:
+      e.synchronize()
+      yield o

@@ -531,6 +531,26 @@ def test_pair_matcher_pipeline_vs_oracle(G, net):
   assert _rel(F, ref) < FEAT_TOL
 
 
+def test_match_many_pipelined_equals_sequential(G, net):
+  """two batches in flight on alternating streams give exactly the results of sequential match() calls"""
+  om, clouds, C_ref, F_in, ref = net
+  from gcl_b200.pipeline import PairMatcher
+  xyz = torch.from_numpy(np.concatenate(clouds)).pin_memory()
+  ptr = torch.tensor([0, len(clouds[0]), len(clouds[0]) + len(clouds[1])])
+  batches = [(xyz, ptr), ((xyz + 0.07).pin_memory(), ptr), ((xyz - 0.11).pin_memory(), ptr), (xyz, ptr)]
+  seq = PairMatcher(om, voxel=0.3, subsample=1000, device=G.dev, seed=9)
+  want = [seq.match(x, p) for x, p in batches]
+  torch.cuda.synchronize()
+  pip = PairMatcher(om, voxel=0.3, subsample=1000, device=G.dev, seed=9)
+  got = list(pip.match_many(iter(batches), depth=2))
+  assert len(got) == len(want)
+  for a, b in zip(got, want):
+    assert a["n_voxels_total"] == b["n_voxels_total"]
+    assert torch.equal(a["feats"], b["feats"]) and torch.equal(a["sel0"], b["sel0"])
+    k = int(b["pair_ptr"][-1])
+    assert torch.equal(a["pair_ptr"], b["pair_ptr"]) and torch.equal(a["pairs"][:k], b["pairs"][:k])
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def _loss_inputs(seed, N=6000, G_=900, C=32):
   rng = np.random.RandomState(seed)
