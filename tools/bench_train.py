@@ -1,0 +1,98 @@
+"""GCL training step on the CUDA operators (BASELINE config 4), timing only -- parity of every piece is covered by
+tests/test_gpu_parity.py (conv fwd/dgrad/wgrad + train-mode BN vs oracle autograd; fused loss fwd/bwd vs the reference's
+trainer).  One step = ResUNetBN2C forward in train mode on a batch of 4 samples x 3 colocated scans (12 clouds), the
+fused finest-contrastive loss (positive groups of 3 + hardest negatives), backward, SGD(momentum .8, wd 1e-4, lr .1)
+(lib/colocation_trainer.py:811-916, config.py:87-96).  Groups are synthetic: the three scans of a sample are jittered
+copies of one 32-beam scan, a group = the rows of the three clouds that share a voxel coordinate.
+
+  python tools/bench_train.py [--steps 10] [--samples 4]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--samples", type=int, default=4)
+  ap.add_argument("--voxel", type=float, default=0.3)
+  args = ap.parse_args()
+  import gcl_b200
+  from gcl_b200 import MinkowskiEngine as ME, ops, synth
+  from gcl_b200.loss import GroupContrastiveLoss, _exhaustive_hash
+  dev = torch.device("cuda:0")
+  torch.manual_seed(0)
+  rng = np.random.RandomState(0)
+  clouds = []
+  for s in range(args.samples):
+    base = synth.cast(synth.Scene(40 + s), synth.NUSCENES, seed=s)
+    for j in range(3):
+      clouds.append((base + rng.normal(0, 0.01, base.shape)).astype(np.float32))
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(dev)
+  ptr = torch.tensor(np.cumsum([0] + [len(c) for c in clouds]))
+  cm, _ = ops.voxelize(xyz, args.voxel, ptr)
+  N = cm.n
+  C = cm.coords
+  # groups: voxel coordinate present in all three clouds of a sample
+  idx_rows, sizes, flags = [], [], []
+  for s in range(args.samples):
+    c0 = C[C[:, 0] == 3 * s]
+    rows0 = torch.nonzero(C[:, 0] == 3 * s)[:, 0]
+    q1, q2 = c0.clone(), c0.clone()
+    q1[:, 0], q2[:, 0] = 3 * s + 1, 3 * s + 2
+    r1, r2 = ops.hash_query(cm, q1), ops.hash_query(cm, q2)
+    ok = (r1 >= 0) & (r2 >= 0)
+    g = torch.stack([rows0[ok], r1[ok].long(), r2[ok].long()], 1)
+    idx_rows.append(g.reshape(-1))
+    sizes.append(torch.full((g.shape[0],), 3, dtype=torch.int64))
+    f = torch.zeros_like(g, dtype=torch.bool); f[:, 0] = True
+    flags.append(f.reshape(-1))
+  index = torch.cat(idx_rows).cpu(); group = torch.cat(sizes); finest = torch.cat(flags).cpu()
+  split = index.numpy().reshape(-1, 3)
+  index_hash = _exhaustive_hash(list(split), N)
+  print(f"clouds={len(clouds)} voxels={N} groups={len(group)}", file=sys.stderr)
+
+  model = gcl_b200.load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, conv1_kernel_size=5, normalize_feature=True).to(dev)
+  model.train()
+  opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
+  crit = GroupContrastiveLoss(pos_thresh=0.1, neg_thresh=1.4, finest_thresh=0.2, square_loss=True,
+                              rng=np.random.RandomState(0))
+  feats = torch.ones(N, 1, device=dev)
+
+  def step():
+    opt.zero_grad(set_to_none=True)
+    st = ME.SparseTensor(feats, coordinates=C)
+    F = model(st).F
+    pos, fin, neg = crit.finest_contrastive_loss(F, group, index, index_hash, finest, max_pos_cluster=256 * args.samples,
+                                                 max_hn_samples=256 * args.samples)
+    loss = pos + fin + neg
+    loss.backward()
+    opt.step()
+    return loss
+
+  for _ in range(2):
+    l0 = step()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    l = step()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / args.steps
+  print(json.dumps({"metric": "gcl_train_step_ms", "value": round(ms, 2), "unit": "ms/step", "clouds": len(clouds), "voxels": N,
+                    "groups": int(len(group)), "loss_first": round(float(l0), 4), "loss_last": round(float(l), 4),
+                    "conv_kernels": "exact-fp32 CUDA-core fwd/dgrad/wgrad (training keeps fp32 arithmetic)"}))
+
+
+if __name__ == "__main__":
+  main()
