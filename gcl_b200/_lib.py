@@ -44,6 +44,7 @@ SIGNATURES = {
     "gclb_subsample": (C.c_int, [_p, _p, _i64, _i32, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),
     "gclb_mutual_filter": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p]),
     "gclb_loss_workspace_bytes": (_sz, [_i64, _i64]),
+    "gclb_debug_tma_gather4": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "gclb_group_loss": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _f32, _f32, _f32,
                                   _i32, _p, _p, _p, _p, _p]),
 }

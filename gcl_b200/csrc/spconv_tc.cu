@@ -4,11 +4,11 @@
 //   one pipeline stage per (populated kernel offset k, 32-channel slab); 4 x tcgen05.mma.kind::tf32 (K = 8) per stage
 //
 // Persistent, warp-specialised CTA (one per SM), 448 threads:
-//   warps 0-7   A producers, one WARP per ring slot (stage it belongs to warp it % STAGES): gather 128 neighbour rows x 128 B with
-//               16-byte cp.async straight into the canonical K-major SWIZZLE_128B layout (row r, chunk j ->
-//               (r/8)*1024 + (r%8)*128 + ((j ^ (r%8))*16)); missing neighbours are zero-filled (src-size 0); lane 0 also
-//               pulls the weight slab with ONE cp.async.bulk (weights are stored pre-swizzled, see gclb_weights_to_tc)
-//               onto the same mbarrier.  Each warp waits only for its own stage => up to 8 stages in flight per SM.
+//   warps 0-7   A producers, one WARP per ring slot (stage it belongs to warp it % STAGES): the 128 neighbour rows x 128 B
+//               of a stage are fetched by 32 TMA tile::gather4 instructions (one per lane, 4 rows each) straight into the
+//               canonical K-major SWIZZLE_128B layout -- the TMA swizzles and zero-fills missing neighbours (index -1 is
+//               out of bounds); lane 0 also pulls the weight slab with ONE cp.async.bulk (weights are stored
+//               pre-swizzled, see gclb_weights_to_tc) onto the same mbarrier.  No LSU traffic, no thread waits for data.
 //   warp  8     one elected thread issues tcgen05.mma; tcgen05.commit recycles smem slots and publishes accumulators.
 //   warp  9     prefetches the next tile's slice of the neighbour table (cp.async) and lists its populated offsets.
 //   warps 10-13 epilogue: tcgen05.ld (thread <-> output row), fused scale/shift (+residual) (+ReLU) (+L2 normalise),
@@ -47,7 +47,9 @@ struct TcShared {   // static shared: barriers + small per-tile metadata
 };
 
 template <int COUT, int KVOL>
-__global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize) {
+__global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
+                                                                      const __grid_constant__ CUtensorMap map0,
+                                                                      const __grid_constant__ CUtensorMap map1) {
   using Cfg = TcCfg<COUT>;
   constexpr int S = Cfg::STAGES;
   constexpr int NBUF = Cfg::NBUF, NACC = Cfg::NACC;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
 
   if (tid == 0) {
     if ((smem_u32(ring) & 1023u) != 0) { printf("gclb spconv_tc: operand ring not 1024-byte aligned\n"); __trap(); }
-    for (int s = 0; s < S; ++s) { mbar_init(&sh.full[s], 2); mbar_init(&sh.empty[s], 1); }   // expect_tx + data-landed
+    for (int s = 0; s < S; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }   // one arrive.expect_tx per stage
     for (int b = 0; b < 4; ++b) {
       mbar_init(&sh.acc_full[b], 1);
       mbar_init(&sh.acc_empty[b], 4);
@@ -87,51 +89,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
 
   if (warp < kGatherWarps) {
     if (warp < S) {
-    // ======================================= A producers: one WARP per pipeline stage ========================
-    // Warp w owns ring slot w (stages it with it % S == w; S <= 8): it gathers the whole 128 x 128 B slab (32 cp.async per
-    // lane), pulls the weight slab with one bulk copy, then waits for ITS OWN data only (wait_group 0 + proxy fence)
-    // and arrives.  Eight warps => up to eight stages in flight per SM; no thread ever stalls behind another stage.
-    const int j = lane & 7;           // 16-byte chunk inside the 128-byte row
-    const int rq = lane >> 3;         // rows rq + 4*q, q = 0..31
+    // ======================================= A producers: TMA gather, one WARP per ring slot ==================
+    // Warp w owns ring slot w (stages it with it % S == w; S <= 8).  Per stage: lane 0 arms the slot's mbarrier with the
+    // stage's byte count and pulls the weight slab with one bulk copy; then every lane issues ONE tile::gather4 (rows
+    // 4*lane .. 4*lane+3 of the tile, 32 channels): 32 TMA instructions move the whole 128 x 128 B operand, swizzled by
+    // the hardware, missing neighbours (-1) zero-filled by the TMA's out-of-bounds rule.  Nothing goes through the
+    // LSU / L1TEX, no thread waits for data: completion arrives on the mbarrier (complete_tx).
     uint32_t it = 0;                  // global stage counter (identical in every role)
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int b = lt % NBUF;
-      const int64_t tile_m = (int64_t)tile * TM;
+      const int tile_m = tile * TM;
       mbar_wait(&sh.nbr_full[b], (lt / NBUF) & 1);
       const int* nb = nbr_buf + b * NBR_INTS;
       const int n_iter = sh.n_act[b] * slabs;
       for (int i = 0; i < n_iter; ++i, ++it) {
-        if ((int)(it % S) != warp) continue;              // ring slot s is always filled by warp s (S <= 8 warps active):
-                                                          // successive rounds of a slot are ordered => no mbarrier phase aliasing
+        if ((int)(it % S) != warp) continue;              // successive rounds of a slot are ordered => no phase aliasing
         const int k = sh.act_k[b][i / slabs];
         const int c = (i % slabs) * KSLAB;
         const int stage = it % S;
+        int r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = identity ? (tile_m + 4 * lane + q) : nb[(4 * lane + q) * KVOL + k];
         mbar_wait(&sh.empty[stage], ((it / S) & 1u) ^ 1u);   // passes immediately during the first round
-        const float* src_base;
-        int src_stride;
-        if (c < p.c0) { src_base = p.in0 + c + j * 4; src_stride = p.c0; }
-        else { src_base = p.in1 + (c - p.c0) + j * 4; src_stride = p.c1; }
         const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
-        if (lane == 0) {   // weight slab: one bulk copy of the pre-swizzled image
-          mbar_arrive_expect_tx(&sh.full[stage], Cfg::B_BYTES);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&sh.full[stage], A_BYTES + Cfg::B_BYTES);
           bulk_g2s(a_s + A_BYTES, p.W + ((size_t)k * slabs + c / KSLAB) * (COUT * KSLAB), Cfg::B_BYTES, &sh.full[stage]);
         }
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-          const int r = rq + 4 * q;
-          int idx;
-          if (identity) idx = (tile_m + r < p.n_out) ? (int)(tile_m + r) : -1;
-          else idx = nb[r * KVOL + k];
-          const bool ok = idx >= 0;
-          const uint32_t dst = a_s + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4);
-          cp_async16(dst, ok ? (const void*)(src_base + (size_t)idx * src_stride) : (const void*)p.in0, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.full[stage]);
+        __syncwarp();                                        // the barrier is armed before any gather can complete on it
+        if (c < p.c0) tma_gather4(a_s + lane * 512, &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
+        else tma_gather4(a_s + lane * 512, &map1, &sh.full[stage], c - p.c0, r[0], r[1], r[2], r[3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.nbr_empty[b]);   // this warp no longer reads the neighbour tile
@@ -312,7 +300,7 @@ __global__ void __launch_bounds__(256) weights_to_tc_kernel(const float* __restr
 }
 
 template <int COUT, int KVOL>
-static int launch_tc(const ConvParams& p, cudaStream_t st) {
+static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   using Cfg = TcCfg<COUT>;
   size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
   auto kern = spconv_fwd_tc_kernel<COUT, KVOL>;
@@ -323,7 +311,11 @@ static int launch_tc(const ConvParams& p, cudaStream_t st) {
   }
   const int num_tiles = (int)((p.n_out + TM - 1) / TM);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;     // persistent: one CTA per SM
-  kern<<<grid, kTcThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1);
+  CUtensorMap map0, map1;
+  int rc = make_rows_tensor_map(&map0, p.in0, n_in, p.c0, 1);
+  if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map(&map1, p.in1, n_in, p.c1, 1) : (map1 = map0, GCLB_OK);
+  if (rc != GCLB_OK) return rc;
+  kern<<<grid, kTcThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: CUDA error: %s", cudaGetErrorString(e));
@@ -342,10 +334,10 @@ bool spconv_tc_supported(const ConvParams& p) {
   return true;
 }
 
-int spconv_fwd_tc(const ConvParams& p, int64_t, cudaStream_t st) {
+int spconv_fwd_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
 #define GCLB_TC_CASE(C) \
   case C:               \
-    return p.K == 27 ? launch_tc<C, 27>(p, st) : launch_tc<C, 1>(p, st);
+    return p.K == 27 ? launch_tc<C, 27>(p, n_in, st) : launch_tc<C, 1>(p, n_in, st);
   switch (p.cout) {
     GCLB_TC_CASE(32)
     GCLB_TC_CASE(64)

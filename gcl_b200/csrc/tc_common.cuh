@@ -1,5 +1,7 @@
 // tcgen05 / mbarrier / cp.async PTX helpers shared by the tensor-core kernels (spconv_tc.cu, nn_tc.cu).  sm_100a only.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gclb {
@@ -97,5 +99,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// TMA tile::gather4: rows r0..r3 x 32 fp32 channels starting at `col` of a row-major [n, c] matrix (tensor map with
+// box {32, 1}, SWIZZLE_128B) land as four consecutive 128-byte rows at `dst`, already swizzled; row indices outside
+// [0, n) are zero-filled by the hardware.  Completion is signalled on `bar` (complete_tx, 512 bytes).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+// host: 2-D fp32 tensor map over a row-major [n, c] matrix, box = 1 row x 32 channels, SWIZZLE_128B  (tma.cu)
+int make_rows_tensor_map(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows);
 
 }  // namespace gclb

@@ -230,6 +230,11 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
                     float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
                     const float* weights, float* losses_out, float* gradF, void* workspace, void* stream);
 
+/* bring-up helper (not on the hot path): one TMA tile::gather4 of rows rows4_host[0..3] x channels [col, col+32) of the
+ * fp32 matrix X [n, c] into a SWIZZLE_128B shared-memory tile, dumped to out256 (device, 256 floats). */
+int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_rows, int32_t col, const int32_t* rows4_host,
+                           float* out256, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
