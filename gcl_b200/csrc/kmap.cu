@@ -8,7 +8,8 @@ namespace gclb {
 __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int32_t* __restrict__ out_c4,
                                                          int64_t n_out, int ksize, int K, int step, int sign,
                                                          int in_stride, int32_t* __restrict__ nbr,
-                                                         int32_t* __restrict__ pair_count, uint8_t* __restrict__ row_keys) {
+                                                         int32_t* __restrict__ pair_count, uint8_t* __restrict__ row_keys,
+                                                         uint32_t* __restrict__ row_masks) {
   extern __shared__ int s_count[];  // [K]
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_count[k] = 0;
   __syncthreads();
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
     const int4 c = c_next;                       // software pipeline: the next row's coordinates are already in flight
     if (o + ostep < n_out) c_next = __ldg(reinterpret_cast<const int4*>(out_c4) + o + ostep);
     int key = 0;
+    unsigned rmask = 0;
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
       int r = -1, ix = 0, iy = 0, iz = 0;
@@ -37,6 +39,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
         nbr[o * K + k] = r;
         if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
       }
+      if (row_masks && k0 == 0) rmask = __ballot_sync(0xffffffffu, r >= 0);   // populated offsets of this row (K <= 32)
       if (row_keys) {   // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
         const bool v = r >= 0;
         key |= __ballot_sync(0xffffffffu, v && ix < half) ? 1 : 0;
@@ -48,6 +51,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
       }
     }
     if (row_keys && lane == 0) row_keys[o] = (uint8_t)key;
+    if (row_masks && lane == 0) row_masks[o] = rmask;
   }
   __syncthreads();
   if (pair_count)
@@ -132,7 +136,9 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_hist_kernel(const int32_
 
 __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n,
                                                                        const int32_t* __restrict__ offs, int64_t nblocks,
-                                                                       int32_t* __restrict__ perm) {
+                                                                       int32_t* __restrict__ perm,
+                                                                       const uint32_t* __restrict__ row_masks,
+                                                                       uint32_t* __restrict__ tile_mask) {
   __shared__ int warp_hist[kCompactBlock / 32][kBuckets];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int e = threadIdx.x; e < (kCompactBlock / 32) * kBuckets; e += kCompactBlock) (&warp_hist[0][0])[e] = 0;
@@ -148,6 +154,10 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uin
     int base = offs[(int64_t)key * nblocks + blockIdx.x];
     for (int w = 0; w < wid; ++w) base += warp_hist[w][key];
     perm[base + rank] = (int32_t)o;                    // stable: buckets keep the original row order
+    if (row_masks && tile_mask) {                      // populated offsets of the 128-row tile this row lands in
+      const unsigned m = __ldg(row_masks + o);
+      if (m) atomicOr(&tile_mask[(base + rank) >> 7], m);
+    }
   }
 }
 
@@ -190,9 +200,10 @@ extern "C" {
 
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
-                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, void* stream) {
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, void* stream) {
   GCLB_CHECK_ARG(in_table && (n_out == 0 || (out_coords4 && nbr)), "null pointer");
   GCLB_CHECK_ARG(in_capacity >= 2 && (in_capacity & (in_capacity - 1)) == 0, "bad capacity");
+  GCLB_CHECK_ARG(row_masks == nullptr || ksize * ksize * ksize <= 32, "row masks need ksize^3 <= 32");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1) &&
                      in_tensor_stride >= 0,
                  "bad kernel geometry");
@@ -202,7 +213,7 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
       make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, in_tensor_stride,
-      nbr, pair_count, row_keys);
+      nbr, pair_count, row_keys, row_masks);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
@@ -235,11 +246,13 @@ size_t gclb_kmap_sort_workspace_bytes(int64_t n_out) {
   return (size_t)(((n_out + 15) & ~15ll) + (kBuckets * nb + 8) * 4);
 }
 
-int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys, int32_t* perm_out,
-                        int32_t* nbr_sorted_out, uint32_t* tile_mask_out, void* workspace, void* stream) {
+int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys,
+                        const uint32_t* row_masks, int32_t* perm_out, int32_t* nbr_sorted_out, uint32_t* tile_mask_out,
+                        void* workspace, void* stream) {
   GCLB_CHECK_ARG(workspace && ksize >= 1 && ksize <= 7, "bad arguments");
   if (n_out == 0) return GCLB_OK;
-  GCLB_CHECK_ARG(nbr && perm_out && nbr_sorted_out, "null pointer");
+  GCLB_CHECK_ARG(nbr && perm_out, "null pointer");
+  GCLB_CHECK_ARG(nbr_sorted_out || !tile_mask_out || row_masks, "tile masks need either the permuted copy or row_masks");
   GCLB_CHECK_ARG(n_out < (1ll << 31), "too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   const int K = ksize * ksize * ksize;
@@ -248,16 +261,22 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
   int32_t* hist = (int32_t*)(keys + ((n_out + 15) & ~15ll));
   rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, row_keys, keys, hist, nb);
   launch_scan_block_counts(hist, kBuckets * nb, nullptr, st);
-  rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out);
-  const int64_t blocks = (n_out * K + 255) / 256;
-  GCLB_CHECK_ARG(blocks < (1ll << 31), "kernel map too large");
   if (tile_mask_out) {
     GCLB_CHECK_ARG(K <= 32, "tile masks need ksize^3 <= 32");
     cudaMemsetAsync(tile_mask_out, 0, (size_t)((n_out + 127) / 128) * 4, st);
   }
-  if (K == 27) permute_rows_kernel<27><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
-  else permute_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tile_mask_out);
-  count_launches(4);
+  const bool masks_in_scatter = tile_mask_out && row_masks;
+  rowkey_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(keys, n_out, hist, nb, perm_out,
+                                                                masks_in_scatter ? row_masks : nullptr,
+                                                                masks_in_scatter ? tile_mask_out : nullptr);
+  if (nbr_sorted_out) {   // optional physical copy of the table in sorted order (the conv kernel can also read through perm)
+    const int64_t blocks = (n_out * K + 255) / 256;
+    GCLB_CHECK_ARG(blocks < (1ll << 31), "kernel map too large");
+    uint32_t* tm = masks_in_scatter ? nullptr : tile_mask_out;
+    if (K == 27) permute_rows_kernel<27><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tm);
+    else permute_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tm);
+  }
+  count_launches(nbr_sorted_out ? 4 : 3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

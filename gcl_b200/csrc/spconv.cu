@@ -387,8 +387,10 @@ int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, 
   GCLB_CHECK_ARG(nbr || K == 1, "nbr may be NULL only for K == 1");
   GCLB_CHECK_ARG(n_in == 0 || in0, "null input");
   GCLB_CHECK_ARG(algo >= 0 && algo <= 2, "algo must be 0, 1 or 2");
-  GCLB_CHECK_ARG(relu >= 0 && relu <= 3, "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows (tcgen05 path, cout == 32)");
-  GCLB_CHECK_ARG(algo == 2 || (relu & 2) == 0, "the fused L2 normalise exists on the tcgen05 path only");
+  GCLB_CHECK_ARG(relu >= 0 && relu <= 7,
+                 "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows, bit 2 = nbr is the re-ordered copy (tcgen05 path)");
+  GCLB_CHECK_ARG(algo == 2 || (relu & 6) == 0, "flag bits 1 and 2 exist on the tcgen05 path only");
+  GCLB_CHECK_ARG((relu & 4) == 0 || row_perm != nullptr, "flag bit 2 needs row_perm");
   GCLB_CHECK_ARG(row_perm == nullptr || (algo == 2 && nbr != nullptr), "row_perm is a tcgen05-path option and needs nbr");
   GCLB_CHECK_ARG(tile_mask == nullptr || (algo == 2 && nbr != nullptr && K <= 32), "tile_mask is a tcgen05-path option");
   if (n_out == 0) return GCLB_OK;

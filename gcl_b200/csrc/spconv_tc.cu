@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   const int cin = p.c0 + p.c1;
   const int slabs = cin / KSLAB;
   const bool identity = (p.nbr == nullptr);     // K == 1 `mm` path: nbr[o] = o
+  const bool nbr_sorted = (p.relu & 4) != 0;    // nbr is the physically re-ordered copy (else: read rows through perm)
 
   if (tid == 0) {
     if ((smem_u32(ring) & 1023u) != 0) { printf("gclb spconv_tc: operand ring not 1024-byte aligned\n"); __trap(); }
@@ -167,14 +168,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
       if (identity) {
         if (lane == 0) sh.act_k[b][0] = 0;
       } else {
-        const int64_t first = (int64_t)tile * NBR_INTS;                  // int index of the tile's first table entry
-        const int64_t total = p.n_out * (int64_t)KVOL;
         const uint32_t nb_u32 = smem_u32(nb);
-        for (int ch = lane; ch < NBR_INTS / 4; ch += 32) {               // 16-byte chunks; the table slice is contiguous
-          int64_t e = first + (int64_t)ch * 4;
-          int64_t left = total - e;                                      // ints still inside the table
-          uint32_t bytes = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
-          cp_async16(nb_u32 + ch * 16, bytes ? (const void*)(p.nbr + e) : (const void*)p.nbr, bytes);
+        if (p.perm && !nbr_sorted) {
+          // the table is in its original order: tile row t is table row perm[tile*128 + t].  Each lane fetches its 4
+          // rows (27 ints = 108 bytes each, 4-byte aligned) with 4-byte cp.async; rows past the end are zero-filled.
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int t = 4 * lane + q;
+            const int64_t t_row = (int64_t)tile * TM + t;
+            const bool in = t_row < p.n_out;
+            const int32_t* src = p.nbr + (in ? (int64_t)__ldg(p.perm + t_row) * KVOL : 0);
+#pragma unroll
+            for (int k = 0; k < KVOL; ++k) cp_async4(nb_u32 + (t * KVOL + k) * 4, src + k, in ? 4u : 0u);
+          }
+        } else {
+          const int64_t first = (int64_t)tile * NBR_INTS;                // int index of the tile's first table entry
+          const int64_t total = p.n_out * (int64_t)KVOL;
+          for (int ch = lane; ch < NBR_INTS / 4; ch += 32) {             // 16-byte chunks; the table slice is contiguous
+            int64_t e = first + (int64_t)ch * 4;
+            int64_t left = total - e;                                    // ints still inside the table
+            uint32_t bytes = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
+            cp_async16(nb_u32 + ch * 16, bytes ? (const void*)(p.nbr + e) : (const void*)p.nbr, bytes);
+          }
         }
         cp_async_commit();
         unsigned m = p.tile_mask ? __ldg(p.tile_mask + tile) : 0u;       // populated offsets, precomputed at sort time

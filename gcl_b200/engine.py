@@ -105,10 +105,12 @@ class ResUNetEngine:
     W, sc, sh = self.p[key]
     if key in self.tc:
       perm = mask = None
-      if isinstance(nbr, tuple):          # (table, sorted table, perm, tile masks) from build_maps
-        nbr, perm, mask = nbr[1], nbr[2], nbr[3]
+      is_sorted = True
+      if isinstance(nbr, tuple):          # (table, sorted copy or None, perm, tile masks) from build_maps
+        table, srt, perm, mask = nbr
+        nbr, is_sorted = (srt, True) if srt is not None else (table, False)
       return ops.spconv_fwd(x, self.tc[key], nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
-                            algo=2, row_perm=perm, tile_mask=mask)
+                            algo=2, row_perm=perm, tile_mask=mask, nbr_is_sorted=is_sorted)
     if isinstance(nbr, tuple):
       nbr = nbr[0]
     return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)
@@ -141,7 +143,9 @@ class ResUNetEngine:
     def table(in_cm, out_cm, ks, transposed=False, tc=True):
       if sort and tc:
         t, keys = ops.kernel_map(in_cm, out_cm, ks, transposed=transposed, with_keys=True)
-        return (t,) + ops.kernel_map_sort(t, keys)
+        # copy=True: a physically re-ordered table.  Reading the original table through the permutation inside the conv
+        # (copy=False, 108 4-byte cp.async per lane per tile) was measured 1.6x slower end to end.
+        return (t,) + ops.kernel_map_sort(t, keys, copy=True)
       return ops.kernel_map(in_cm, out_cm, ks, transposed=transposed)
 
     recipes = {}

@@ -161,11 +161,12 @@ def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1,
   nbr = torch.empty((out_cm.n, K), dtype=torch.int32, device=dev)
   counts = torch.zeros(K, dtype=torch.int32, device=dev) if count_pairs else None
   keys = torch.empty(out_cm.n, dtype=torch.uint8, device=dev) if with_keys else None
+  masks = torch.empty(out_cm.n, dtype=torch.int32, device=dev) if (with_keys and K <= 32) else None
   step = out_cm.tensor_stride if transposed else in_cm.tensor_stride
   call("gclb_kmap_build", ptr(in_cm.table), in_cm.capacity, ptr(out_cm.coords), out_cm.n, ksize, step, dilation,
-       -1 if transposed else 1, in_cm.tensor_stride, ptr(nbr), ptr(counts), ptr(keys), stream())
+       -1 if transposed else 1, in_cm.tensor_stride, ptr(nbr), ptr(counts), ptr(keys), ptr(masks), stream())
   if with_keys:
-    return nbr, keys
+    return nbr, (keys, masks)
   return (nbr, counts) if count_pairs else nbr
 
 
@@ -183,25 +184,32 @@ def kernel_map_pairs(nbr: torch.Tensor):
   return in_idx[:total], out_idx[:total], off
 
 
-def kernel_map_sort(nbr: torch.Tensor, keys: Optional[torch.Tensor] = None):
+def kernel_map_sort(nbr: torch.Tensor, keys=None, copy: bool = True):
   """Group table rows by neighbour-direction pattern for the tcgen05 kernel: returns (nbr_sorted, perm, tile_mask) with
-  nbr_sorted[t] = nbr[perm[t]] and tile_mask[t // 128] = bit mask of the offsets populated in that 128-row tile."""
+  nbr_sorted[t] = nbr[perm[t]] and tile_mask[t // 128] = bit mask of the offsets populated in that 128-row tile.
+  keys: the (row_keys, row_masks) pair from kernel_map(with_keys=True).  copy=False skips the physical copy
+  (nbr_sorted is None): the conv kernel then reads rows of the original table through `perm` (needs row_masks)."""
   n_out, K = nbr.shape
   ksize = round(K ** (1 / 3))
   assert ksize ** 3 == K
   lib = _lib.load()
   perm = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
-  out = torch.empty_like(nbr)
+  row_keys, row_masks = keys if keys is not None else (None, None)
+  if not copy:
+    assert row_masks is not None, "copy=False needs the row masks from kernel_map(with_keys=True)"
+  out = torch.empty_like(nbr) if copy else None
   mask = torch.empty((n_out + 127) // 128, dtype=torch.int32, device=nbr.device) if K <= 32 else None
   ws = _workspace(lib.gclb_kmap_sort_workspace_bytes(n_out), nbr.device)
-  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(keys), ptr(perm), ptr(out), ptr(mask), ptr(ws), stream())
+  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(row_keys), ptr(row_masks), ptr(perm), ptr(out), ptr(mask),
+       ptr(ws), stream())
   return out, perm, mask
 
 
 def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
                out: Optional[torch.Tensor] = None, algo: int = 0, normalize: bool = False,
-               row_perm: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+               row_perm: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None,
+               nbr_is_sorted: bool = True) -> torch.Tensor:
   """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path); with algo=2 (tcgen05) W is the
   tensor-core layout [K, Cout, Cin] from `weights_to_tc`."""
   require_cuda(in0, W, nbr, in1, scale, shift, residual)
@@ -219,9 +227,9 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
     assert nbr.dtype == torch.int32 and tuple(nbr.shape) == (n_out, K)
   if out is None:
     out = torch.empty((n_out, cout), dtype=torch.float32, device=in0.device)
+  flags = int(bool(relu)) | (2 if normalize else 0) | (4 if (row_perm is not None and nbr_is_sorted) else 0)
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
-       ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)) | (2 if normalize else 0), ptr(out), n_out, algo,
-       stream())
+       ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), flags, ptr(out), n_out, algo, stream())
   return out
 
 

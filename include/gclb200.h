@@ -106,10 +106,12 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
  *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
  *   row_keys uint8 [n_out] or NULL: 6-bit neighbour-direction key of every row, computed for free during the build
  *            and accepted by gclb_kmap_sort_rows.
+ *   row_masks uint32 [n_out] or NULL (ksize^3 <= 32): bit k set iff nbr[o, k] >= 0; lets gclb_kmap_sort_rows derive
+ *            the per-tile masks without re-reading the table.
  * ---------------------------------------------------------------------------------------------------- */
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
-                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, void* stream);
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, void* stream);
 /* expand a neighbour table into ME-style per-offset pair lists, canonical order (k ascending, out row
  * ascending): in_idx/out_idx int32 [n_out*K] (first offset_ptr[K] valid), offset_ptr int64 [K+1]. */
 int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_idx, int32_t* out_idx,
@@ -121,8 +123,8 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
  * both to gclb_spconv_fwd(algo=2); results are identical, the kernel just runs ~2-8x fewer pipeline stages. */
 size_t gclb_kmap_sort_workspace_bytes(int64_t n_out);
 int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys /* or NULL */,
-                        int32_t* perm_out, int32_t* nbr_sorted_out, uint32_t* tile_mask_out, void* workspace,
-                        void* stream);
+                        const uint32_t* row_masks /* or NULL */, int32_t* perm_out, int32_t* nbr_sorted_out /* or NULL */,
+                        uint32_t* tile_mask_out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K3 sparse convolution forward, output-stationary implicit GEMM with fused epilogue
@@ -132,12 +134,14 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
  *   in0 [n_in, c0], in1 [n_in, c1] or NULL : the input is the channel concatenation [in0 | in1] (ME.cat fused)
  *   W  float32 [K, c0+c1, cout]            : ME layout (Appendix A10)
  *   nbr int32 [n_out, K] or NULL (K==1: identity map, the kernel_size==1 `F.mm` path)
- *   row_perm int32 [n_out] or NULL: tcgen05 path only -- row t of `nbr` then describes OUTPUT row row_perm[t]
- *            (tables re-ordered by gclb_kmap_sort_rows so that a 128-row tile touches few kernel offsets)
+ *   row_perm int32 [n_out] or NULL: tcgen05 path only -- tile row t processes OUTPUT row row_perm[t] (ordering from
+ *            gclb_kmap_sort_rows so that a 128-row tile touches few kernel offsets).  relu bit 2 (value 4) says `nbr`
+ *            is the physically re-ordered copy (row t of nbr describes output row row_perm[t]); without it `nbr` is the
+ *            original table and the kernel reads row row_perm[t] of it.
  *   tile_mask uint32 [ceil(n_out/128)] or NULL: tcgen05 path only -- populated-offset bit mask per 128-row tile of
  *            `nbr` (from gclb_kmap_sort_rows); saves the kernel an in-tile scan
  *   scale, shift float32 [cout] or NULL    : folded eval-mode BatchNorm / bias
- *   residual float32 [n_out, cout] or NULL ; relu: bit 0 = ReLU, bit 1 = divide every output row by its L2 norm
+ *   residual float32 [n_out, cout] or NULL ; relu (flags): bit 0 = ReLU, bit 1 = divide every output row by its L2 norm
  *   afterwards (model/resunet.py:226-230; tcgen05 path with cout == 32 only)
  *   algo: 0/1 = fp32 CUDA-core kernel (exact fp32; any channel counts);
  *         2   = tcgen05 kind::tf32 tensor-core kernel, fp32 accumulate in TMEM.  W must then be in the tensor-core

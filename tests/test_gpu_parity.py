@@ -238,8 +238,12 @@ def test_kmap_row_bucketing_is_a_pure_reordering(G):
   C_ref, _ = _oracle_voxelize([_random_cloud(24, 9000, 12.0), _random_cloud(25, 500, 3.0)], 0.3)
   cm = G.ops.hash_build(C_ref.to(G.dev))
   cm2 = G.ops.stride_map(cm, 2)
-  for nbr in (G.ops.kernel_map(cm, cm, 3), G.ops.kernel_map(cm2, cm, 3, transposed=True), G.ops.kernel_map(cm, cm2, 3)):
+  for args in ((cm, cm, 3, 1, False), (cm2, cm, 3, 1, True), (cm, cm2, 3, 1, False)):
+    nbr, keys = G.ops.kernel_map(*args, with_keys=True)
     srt, perm, mask = G.ops.kernel_map_sort(nbr)
+    none, perm2, mask2 = G.ops.kernel_map_sort(nbr, keys, copy=False)      # keys + row masks straight from the build
+    assert none is None and torch.equal(perm, perm2) and torch.equal(mask, mask2)
+    assert torch.equal(keys[1], ((nbr >= 0).int() << torch.arange(27, device=G.dev, dtype=torch.int32)).sum(1).int())
     n = nbr.shape[0]
     assert torch.equal(torch.sort(perm.long()).values.cpu(), torch.arange(n))
     assert torch.equal(srt, nbr[perm.long()])
@@ -258,7 +262,8 @@ def test_kmap_row_bucketing_is_a_pure_reordering(G):
     a = G.ops.spconv_fwd(x, Wt, nbr, n, algo=2)
     b = G.ops.spconv_fwd(x, Wt, srt, n, algo=2, row_perm=perm)
     c = G.ops.spconv_fwd(x, Wt, srt, n, algo=2, row_perm=perm, tile_mask=mask)
-    assert torch.equal(a, b) and torch.equal(a, c)
+    d = G.ops.spconv_fwd(x, Wt, nbr, n, algo=2, row_perm=perm, tile_mask=mask, nbr_is_sorted=False)   # table read through perm
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d)
     want_mask = [int(sum(1 << k for k in range(27) if v[t:t + 128, k].any())) for t in range(0, n, 128)]
     assert mask.tolist() == want_mask
 
