@@ -212,7 +212,15 @@ def cat(*tensors):
 
 # Which convolution kernel the module path uses.  Training (autograd active) always runs the exact-fp32 kernels so that
 # gradients match the reference's fp32 arithmetic; inference uses the tcgen05 kind::tf32 kernel where it applies.
-_CONV_ALGO = {"inference": "auto"}
+_CONV_ALGO = {"inference": "auto", "training": "fp32"}
+
+
+def set_training_conv_algo(name: str):
+  """'fp32' (default: exact-fp32 forward / dgrad / wgrad, gradients match the reference's arithmetic to ~1e-5) or 'tf32'
+  (forward and dgrad on the tcgen05 kind::tf32 kernel where the layer shape allows, ~1e-3; wgrad stays fp32)."""
+  if name not in ("fp32", "tf32"):
+    raise ValueError("algo must be 'fp32' or 'tf32'")
+  _CONV_ALGO["training"] = name
 
 
 def set_inference_conv_algo(name: str):
@@ -229,13 +237,21 @@ class MinkowskiNetwork(nn.Module):
 
 
 class _SparseConvFn(torch.autograd.Function):
-  """out = conv(x, W) over a neighbour table; backward = dgrad (same kernel, transposed table/weights) + wgrad."""
+  """out = conv(x, W) over a neighbour table; backward = dgrad (same kernel, dual table / transposed weights) + wgrad.
+  `tc_fwd` / `tc_bwd` are row-bucketed tables (sorted, perm, masks) when the tcgen05 kernel should be used."""
 
   @staticmethod
-  def forward(ctx, x, W, nbr_fwd, nbr_bwd, n_out, mirror):
+  def forward(ctx, x, W, nbr_fwd, nbr_bwd, n_out, mirror, tc_fwd, tc_bwd):
     ctx.save_for_backward(x, W)
-    ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.n_in = nbr_fwd, nbr_bwd, mirror, x.shape[0]
-    return ops.spconv_fwd(x.contiguous(), W, nbr_fwd, n_out)
+    ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.n_in, ctx.tc_bwd = nbr_fwd, nbr_bwd, mirror, x.shape[0], tc_bwd
+    xc = x.contiguous()
+    if tc_fwd is not None:
+      Wt = ops.weights_to_tc(W.detach())
+      if tc_fwd == "mm":
+        return ops.spconv_fwd(xc, Wt, None, n_out, algo=2)
+      srt, perm, mask = tc_fwd
+      return ops.spconv_fwd(xc, Wt, srt, n_out, algo=2, row_perm=perm, tile_mask=mask)
+    return ops.spconv_fwd(xc, W, nbr_fwd, n_out)
 
   @staticmethod
   def backward(ctx, gout):
@@ -245,11 +261,19 @@ class _SparseConvFn(torch.autograd.Function):
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     if ctx.needs_input_grad[0]:
       # mirror: stride-1 odd kernels reuse the forward table with offsets reversed (k -> K-1-k)
-      Wt = (W3.flip(0) if ctx.mirror else W3).transpose(1, 2).contiguous()
-      gx = ops.spconv_fwd(gout, Wt, ctx.nbr_bwd, ctx.n_in)
+      Wd = (W3.flip(0) if ctx.mirror else W3).transpose(1, 2).contiguous()       # [K, Cout, Cin]
+      if ctx.tc_bwd is not None:
+        Wt = ops.weights_to_tc(Wd)
+        if ctx.tc_bwd == "mm":
+          gx = ops.spconv_fwd(gout, Wt, None, ctx.n_in, algo=2)
+        else:
+          srt, perm, mask = ctx.tc_bwd
+          gx = ops.spconv_fwd(gout, Wt, srt, ctx.n_in, algo=2, row_perm=perm, tile_mask=mask)
+      else:
+        gx = ops.spconv_fwd(gout, Wd, ctx.nbr_bwd, ctx.n_in)
     if ctx.needs_input_grad[1]:
       gW = ops.spconv_wgrad(x, gout, ctx.nbr_fwd, W3.shape[0]).view_as(W)
-    return gx, gW, None, None, None, None
+    return gx, gW, None, None, None, None, None, None
 
 
 class _ConvBase(nn.Module):
@@ -308,10 +332,18 @@ class _ConvBase(nn.Module):
     n_out = mgr.size(out_key)
     needs_grad = torch.is_grad_enabled() and (x.F.requires_grad or self.kernel.requires_grad)
     if needs_grad:
+      dual = (out_key, in_key, self.kernel_size, self.dilation, not self.TRANSPOSED)
       if nbr_b is None and not self.use_mm and x.F.requires_grad:
         # dgrad table: the same pairs, indexed by input row (strided <-> transposed swap)
-        nbr_b = mgr.kernel_map(out_key, in_key, self.kernel_size, self.dilation, not self.TRANSPOSED)
-      out = _SparseConvFn.apply(x.F, self.kernel, nbr_f, nbr_b, n_out, mirror)
+        nbr_b = mgr.kernel_map(*dual)
+      tc_f = tc_b = None
+      if _CONV_ALGO["training"] == "tf32":
+        fwd_key = (in_key, out_key, self.kernel_size, self.dilation, self.TRANSPOSED)
+        if ops.tc_supported(self.in_channels, 0, self.out_channels, self.kernel_volume):
+          tc_f = "mm" if self.use_mm else mgr.kernel_map_sorted(*fwd_key)
+        if x.F.requires_grad and ops.tc_supported(self.out_channels, 0, self.in_channels, self.kernel_volume):
+          tc_b = "mm" if self.use_mm else mgr.kernel_map_sorted(*(fwd_key if mirror else dual))
+      out = _SparseConvFn.apply(x.F, self.kernel, nbr_f, nbr_b, n_out, mirror, tc_f, tc_b)
       if self.bias is not None:
         out = out + self.bias
     else:

@@ -25,11 +25,14 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--samples", type=int, default=4)
   ap.add_argument("--voxel", type=float, default=0.3)
+  ap.add_argument("--tf32", action="store_true", help="forward + dgrad on the tcgen05 kind::tf32 kernel")
   args = ap.parse_args()
   import gcl_b200
   from gcl_b200 import MinkowskiEngine as ME, ops, synth
   from gcl_b200.loss import GroupContrastiveLoss, _exhaustive_hash
   dev = torch.device("cuda:0")
+  if args.tf32:
+    ME.set_training_conv_algo("tf32")
   torch.manual_seed(0)
   rng = np.random.RandomState(0)
   clouds = []
@@ -91,7 +94,8 @@ def main():
   ms = e0.elapsed_time(e1) / args.steps
   print(json.dumps({"metric": "gcl_train_step_ms", "value": round(ms, 2), "unit": "ms/step", "clouds": len(clouds), "voxels": N,
                     "groups": int(len(group)), "loss_first": round(float(l0), 4), "loss_last": round(float(l), 4),
-                    "conv_kernels": "exact-fp32 CUDA-core fwd/dgrad/wgrad (training keeps fp32 arithmetic)"}))
+                    "conv_kernels": ("tcgen05 kind::tf32 fwd + dgrad, fp32 wgrad" if args.tf32 else
+                                     "exact-fp32 CUDA-core fwd/dgrad/wgrad")}))
 
 
 if __name__ == "__main__":
