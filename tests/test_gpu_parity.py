@@ -268,6 +268,27 @@ def test_kmap_row_bucketing_is_a_pure_reordering(G):
     assert mask.tolist() == want_mask
 
 
+def test_tma_gather4_primitive(G):
+  """the TMA tile::gather4 load the conv kernel is built on: 4 arbitrary rows x 32 channels land as consecutive
+  SWIZZLE_128B rows (16-byte chunk j of row r at r*128 + ((j ^ r) << 4)); out-of-range rows are zero-filled"""
+  import ctypes
+  from gcl_b200 import _lib
+  lib = _lib.load()
+  n, c = 777, 96
+  X = torch.arange(n * c, dtype=torch.float32, device=G.dev).reshape(n, c)
+  for rows, col in (([5, 17, 700, 3], 32), ([0, -1, 9999, 776], 64)):
+    out = torch.full((256,), -1.0, device=G.dev)
+    r = (ctypes.c_int32 * 4)(*rows)
+    assert lib.gclb_debug_tma_gather4(X.data_ptr(), n, c, 1, col, ctypes.cast(r, ctypes.c_void_p), out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    o = out.cpu().reshape(8, 8, 4)          # [smem row, 16-byte chunk, float]
+    for i, row in enumerate(rows):
+      for j in range(8):
+        want = (X[row, col + 4 * j: col + 4 * j + 4].cpu() if 0 <= row < n else torch.zeros(4))
+        assert torch.equal(o[i, j ^ i], want)
+    assert bool((o[4:] == -777.0).all())     # nothing beyond the four rows is written
+
+
 def test_tc_two_source_epilogue(G):
   torch.manual_seed(6)
   C_ref, _ = _oracle_voxelize([_random_cloud(23, 5000, 9.0)], 0.3)
