@@ -26,10 +26,10 @@ SIGNATURES = {
     "gclb_voxelize": (C.c_int, [_p, _i64, _p, _i32, _f32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_quantize_rows": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_stride_map": (C.c_int, [_p, _i64, _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p]),
-    "gclb_kmap_build": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "gclb_kmap_build": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "gclb_kmap_pairs": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "gclb_kmap_sort_workspace_bytes": (_sz, [_i64]),
-    "gclb_kmap_sort_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "gclb_kmap_sort_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_spconv_fwd": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64,
                                   _i32, _p]),
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,

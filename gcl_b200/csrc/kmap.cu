@@ -9,7 +9,8 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
                                                          int64_t n_out, int ksize, int K, int step, int sign,
                                                          int in_stride, int32_t* __restrict__ nbr,
                                                          int32_t* __restrict__ pair_count, uint8_t* __restrict__ row_keys,
-                                                         uint32_t* __restrict__ row_masks) {
+                                                         uint32_t* __restrict__ row_masks, int32_t* __restrict__ key_hist,
+                                                         int64_t hist_blocks) {
   extern __shared__ int s_count[];  // [K]
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_count[k] = 0;
   __syncthreads();
@@ -50,7 +51,10 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
         key |= __ballot_sync(0xffffffffu, v && iz > half) ? 32 : 0;
       }
     }
-    if (row_keys && lane == 0) row_keys[o] = (uint8_t)key;
+    if (row_keys && lane == 0) {
+      row_keys[o] = (uint8_t)key;
+      if (key_hist) atomicAdd(&key_hist[(int64_t)key * hist_blocks + (o >> 10)], 1);   // [bucket][1024-row block] counts
+    }
     if (row_masks && lane == 0) row_masks[o] = rmask;
   }
   __syncthreads();
@@ -134,15 +138,37 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_hist_kernel(const int32_
   if (threadIdx.x < kBuckets) hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // bucket-major
 }
 
+// Stable scatter with the scan fused in: every block derives its own bucket bases from the raw [bucket][block] histogram
+// (16 threads per bucket sum the blocks before it and all blocks), so no separate scan launch is needed.
 __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n,
-                                                                       const int32_t* __restrict__ offs, int64_t nblocks,
+                                                                       const int32_t* __restrict__ hist, int64_t nblocks,
                                                                        int32_t* __restrict__ perm,
                                                                        const uint32_t* __restrict__ row_masks,
                                                                        uint32_t* __restrict__ tile_mask) {
   __shared__ int warp_hist[kCompactBlock / 32][kBuckets];
+  __shared__ int s_prefix[kBuckets], s_total[kBuckets], s_base[kBuckets];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int e = threadIdx.x; e < (kCompactBlock / 32) * kBuckets; e += kCompactBlock) (&warp_hist[0][0])[e] = 0;
+  {
+    const int bucket = threadIdx.x >> 4, sub = threadIdx.x & 15;       // 1024 threads = 64 buckets x 16
+    int pre = 0, tot = 0;
+    for (int64_t blk = sub; blk < nblocks; blk += 16) {
+      const int v = __ldg(&hist[(int64_t)bucket * nblocks + blk]);
+      tot += v;
+      if (blk < blockIdx.x) pre += v;
+    }
+#pragma unroll
+    for (int m = 1; m < 16; m <<= 1) {
+      pre += __shfl_xor_sync(0xffffffffu, pre, m);
+      tot += __shfl_xor_sync(0xffffffffu, tot, m);
+    }
+    if (sub == 0) { s_prefix[bucket] = pre; s_total[bucket] = tot; }
+  }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int bkt = 0; bkt < kBuckets; ++bkt) { s_base[bkt] = run + s_prefix[bkt]; run += s_total[bkt]; }
+  }
   int64_t o = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
   const bool valid = o < n;
   const int key = valid ? keys[o] : kBuckets;          // invalid lanes form their own group
@@ -151,7 +177,7 @@ __global__ void __launch_bounds__(kCompactBlock) rowkey_scatter_kernel(const uin
   if (valid && rank == 0) warp_hist[wid][key] = __popc(same);
   __syncthreads();
   if (valid) {
-    int base = offs[(int64_t)key * nblocks + blockIdx.x];
+    int base = s_base[key];
     for (int w = 0; w < wid; ++w) base += warp_hist[w][key];
     perm[base + rank] = (int32_t)o;                    // stable: buckets keep the original row order
     if (row_masks && tile_mask) {                      // populated offsets of the 128-row tile this row lands in
@@ -200,10 +226,12 @@ extern "C" {
 
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
-                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, void* stream) {
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist,
+                    void* stream) {
   GCLB_CHECK_ARG(in_table && (n_out == 0 || (out_coords4 && nbr)), "null pointer");
   GCLB_CHECK_ARG(in_capacity >= 2 && (in_capacity & (in_capacity - 1)) == 0, "bad capacity");
   GCLB_CHECK_ARG(row_masks == nullptr || ksize * ksize * ksize <= 32, "row masks need ksize^3 <= 32");
+  GCLB_CHECK_ARG(key_hist == nullptr || row_keys != nullptr, "key_hist needs row_keys");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1) &&
                      in_tensor_stride >= 0,
                  "bad kernel geometry");
@@ -213,7 +241,7 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
       make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, in_tensor_stride,
-      nbr, pair_count, row_keys, row_masks);
+      nbr, pair_count, row_keys, row_masks, key_hist, compact_blocks(n_out));
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
@@ -247,8 +275,8 @@ size_t gclb_kmap_sort_workspace_bytes(int64_t n_out) {
 }
 
 int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys,
-                        const uint32_t* row_masks, int32_t* perm_out, int32_t* nbr_sorted_out, uint32_t* tile_mask_out,
-                        void* workspace, void* stream) {
+                        const uint32_t* row_masks, const int32_t* key_hist, int32_t* perm_out, int32_t* nbr_sorted_out,
+                        uint32_t* tile_mask_out, void* workspace, void* stream) {
   GCLB_CHECK_ARG(workspace && ksize >= 1 && ksize <= 7, "bad arguments");
   if (n_out == 0) return GCLB_OK;
   GCLB_CHECK_ARG(nbr && perm_out, "null pointer");
@@ -259,8 +287,15 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
   const int64_t nb = compact_blocks(n_out);
   uint8_t* keys = (uint8_t*)workspace;
   int32_t* hist = (int32_t*)(keys + ((n_out + 15) & ~15ll));
-  rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, row_keys, keys, hist, nb);
-  launch_scan_block_counts(hist, kBuckets * nb, nullptr, st);
+  GCLB_CHECK_ARG(key_hist == nullptr || row_keys != nullptr, "key_hist comes with row_keys (both from gclb_kmap_build)");
+  int launches = nbr_sorted_out ? 2 : 1;
+  if (key_hist) {        // keys and their per-block histogram were produced by gclb_kmap_build: nothing to recompute
+    keys = const_cast<uint8_t*>(row_keys);
+    hist = const_cast<int32_t*>(key_hist);
+  } else {
+    rowkey_hist_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(nbr, n_out, ksize, K, row_keys, keys, hist, nb);
+    ++launches;
+  }
   if (tile_mask_out) {
     GCLB_CHECK_ARG(K <= 32, "tile masks need ksize^3 <= 32");
     cudaMemsetAsync(tile_mask_out, 0, (size_t)((n_out + 127) / 128) * 4, st);
@@ -276,7 +311,7 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
     if (K == 27) permute_rows_kernel<27><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tm);
     else permute_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nbr, perm_out, n_out, K, nbr_sorted_out, tm);
   }
-  count_launches(nbr_sorted_out ? 4 : 3);
+  count_launches(launches);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

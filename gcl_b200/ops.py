@@ -162,11 +162,12 @@ def kernel_map(in_cm: CoordMap, out_cm: CoordMap, ksize: int, dilation: int = 1,
   counts = torch.zeros(K, dtype=torch.int32, device=dev) if count_pairs else None
   keys = torch.empty(out_cm.n, dtype=torch.uint8, device=dev) if with_keys else None
   masks = torch.empty(out_cm.n, dtype=torch.int32, device=dev) if (with_keys and K <= 32) else None
+  hist = torch.zeros((64, (out_cm.n + 1023) // 1024), dtype=torch.int32, device=dev) if with_keys else None
   step = out_cm.tensor_stride if transposed else in_cm.tensor_stride
   call("gclb_kmap_build", ptr(in_cm.table), in_cm.capacity, ptr(out_cm.coords), out_cm.n, ksize, step, dilation,
-       -1 if transposed else 1, in_cm.tensor_stride, ptr(nbr), ptr(counts), ptr(keys), ptr(masks), stream())
+       -1 if transposed else 1, in_cm.tensor_stride, ptr(nbr), ptr(counts), ptr(keys), ptr(masks), ptr(hist), stream())
   if with_keys:
-    return nbr, (keys, masks)
+    return nbr, (keys, masks, hist)
   return (nbr, counts) if count_pairs else nbr
 
 
@@ -194,14 +195,14 @@ def kernel_map_sort(nbr: torch.Tensor, keys=None, copy: bool = True):
   assert ksize ** 3 == K
   lib = _lib.load()
   perm = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
-  row_keys, row_masks = keys if keys is not None else (None, None)
+  row_keys, row_masks, key_hist = keys if keys is not None else (None, None, None)
   if not copy:
     assert row_masks is not None, "copy=False needs the row masks from kernel_map(with_keys=True)"
   out = torch.empty_like(nbr) if copy else None
   mask = torch.empty((n_out + 127) // 128, dtype=torch.int32, device=nbr.device) if K <= 32 else None
   ws = _workspace(lib.gclb_kmap_sort_workspace_bytes(n_out), nbr.device)
-  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(row_keys), ptr(row_masks), ptr(perm), ptr(out), ptr(mask),
-       ptr(ws), stream())
+  call("gclb_kmap_sort_rows", ptr(nbr), n_out, ksize, ptr(row_keys), ptr(row_masks), ptr(key_hist), ptr(perm), ptr(out),
+       ptr(mask), ptr(ws), stream())
   return out, perm, mask
 
 

@@ -106,12 +106,15 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
  *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
  *   row_keys uint8 [n_out] or NULL: 6-bit neighbour-direction key of every row, computed for free during the build
  *            and accepted by gclb_kmap_sort_rows.
+ *   key_hist int32 [64, ceil(n_out/1024)] or NULL (caller-zeroed, needs row_keys): histogram of the row keys per
+ *            1024-row block, accumulated during the build; gclb_kmap_sort_rows then needs no counting pass.
  *   row_masks uint32 [n_out] or NULL (ksize^3 <= 32): bit k set iff nbr[o, k] >= 0; lets gclb_kmap_sort_rows derive
  *            the per-tile masks without re-reading the table.
  * ---------------------------------------------------------------------------------------------------- */
 int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* out_coords4, int64_t n_out,
                     int32_t ksize, int32_t offset_stride, int32_t dilation, int32_t sign, int32_t in_tensor_stride,
-                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, void* stream);
+                    int32_t* nbr, int32_t* pair_count, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist,
+                    void* stream);
 /* expand a neighbour table into ME-style per-offset pair lists, canonical order (k ascending, out row
  * ascending): in_idx/out_idx int32 [n_out*K] (first offset_ptr[K] valid), offset_ptr int64 [K+1]. */
 int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_idx, int32_t* out_idx,
@@ -123,8 +126,8 @@ int gclb_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* in_id
  * both to gclb_spconv_fwd(algo=2); results are identical, the kernel just runs ~2-8x fewer pipeline stages. */
 size_t gclb_kmap_sort_workspace_bytes(int64_t n_out);
 int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const uint8_t* row_keys /* or NULL */,
-                        const uint32_t* row_masks /* or NULL */, int32_t* perm_out, int32_t* nbr_sorted_out /* or NULL */,
-                        uint32_t* tile_mask_out, void* workspace, void* stream);
+                        const uint32_t* row_masks /* or NULL */, const int32_t* key_hist /* or NULL */, int32_t* perm_out,
+                        int32_t* nbr_sorted_out /* or NULL */, uint32_t* tile_mask_out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K3 sparse convolution forward, output-stationary implicit GEMM with fused epilogue
