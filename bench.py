@@ -316,9 +316,10 @@ def main():
 
   for s in range(args.warmup):
     step_resident(s)
-  if args.depth > 1:
-    for out in matcher.match_many((resident[i % n_batches] for i in range(args.depth + 1)), depth=args.depth):
-      pass
+  if args.depth > 1:   # warm the per-stream allocator pools of the pipelined path with every batch shape
+    for src in (resident, pinned):
+      for out in matcher.match_many((src[i % n_batches] for i in range(2 * n_batches * args.depth)), depth=args.depth):
+        pass
   clocks = ClockSampler(local_rank)
   if rank == 0:
     clocks.start()

@@ -44,7 +44,7 @@ for row in rows:
   a["regs"] = int(g(row, "launch__registers_per_thread"))
 tot = sum(a["t"] for a in agg.values())
 print(f"# {title}\n")
-print("One bench step (8 KITTI-shape scan pairs, ~325k voxels) under `ncu` (serialised, cold caches: compare shares, not "
+print("One bench step (16 KITTI-shape scan pairs, ~650k voxels) under `ncu` (serialised, cold caches: compare shares, not "
       "absolutes). Percentages are time-weighted means over the launches of a kernel; DRAM = read + write bytes.\n")
 print("| kernel | launches | time us | share | DRAM MB | DRAM GB/s | DRAM % | L2 % | tensor pipe % | SM % | warps active % | regs |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
