@@ -214,7 +214,7 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--steps", type=int, default=50)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--pairs", type=int, default=16, help="scan pairs per step per GPU")
   ap.add_argument("--depth", type=int, default=2, help="batches in flight (PairMatcher.match_many); 1 = plain match() calls")
