@@ -61,3 +61,33 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket
     if size >= bucket_bytes:
       flush()
   flush()
+
+
+class FlatGradients:
+  """Gradient storage for the data-parallel training step: ONE flat fp32 buffer, every `p.grad` a view into it, so the
+  exchange step is a single in-place NCCL all-reduce (AVG) with no pack/unpack copies (35 MB for ResUNetBN2C, one launch
+  over NVSwitch).  autograd accumulates into an existing `.grad` in place, so the views survive `backward()`; call
+  `zero()` instead of `optimizer.zero_grad(set_to_none=True)`."""
+
+  def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+    self.params = [p for p in params if p.requires_grad]
+    self.group = group
+    total = sum(p.numel() for p in self.params)
+    ref = self.params[0]
+    self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+    off = 0
+    for p in self.params:
+      p.grad = self.flat[off:off + p.numel()].view_as(p)
+      off += p.numel()
+
+  def zero(self):
+    self.flat.zero_()
+
+  def allreduce(self):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+      return
+    if dist.get_backend(self.group) == "nccl":
+      dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+    else:  # gloo has no AVG
+      dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+      self.flat.div_(dist.get_world_size(self.group))

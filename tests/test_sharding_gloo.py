@@ -25,6 +25,19 @@ def _worker(rank, world, port, q):
   lin(x).sum().backward()
   local = [p.grad.clone() for p in lin.parameters()]
   allreduce_gradients(lin.parameters(), bucket_bytes=1 << 16)   # forces several buckets
+  # same exchange through the flat-view buffer the training step uses: views must survive backward(), result identical
+  from gcl_b200.sharding import FlatGradients
+  lin2 = torch.nn.Linear(300, 200)
+  lin2.load_state_dict(lin.state_dict())
+  fg = FlatGradients(lin2.parameters())
+  for _ in range(2):  # second pass checks zero() + in-place accumulation
+    fg.zero()
+    lin2(x).sum().backward()
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad.data_ptr() < fg.flat.data_ptr() + fg.flat.numel() * 4
+               for p in lin2.parameters())
+    fg.allreduce()
+  for a, b in zip(lin.parameters(), lin2.parameters()):
+    assert torch.allclose(a.grad, b.grad)
   q.put((rank, units, ms, [p.grad.clone() for p in lin.parameters()], local))
   dist.barrier()
   dist.destroy_process_group()

@@ -5,7 +5,13 @@ fused finest-contrastive loss (positive groups of 3 + hardest negatives), backwa
 (lib/colocation_trainer.py:811-916, config.py:87-96).  Groups are synthetic: the three scans of a sample are jittered
 copies of one 32-beam scan, a group = the rows of the three clouds that share a voxel coordinate.
 
-  python tools/bench_train.py [--steps 10] [--samples 4]
+  python tools/bench_train.py [--steps 10] [--samples 4] [--tf32]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+      tools/bench_train.py --tf32        # N ranks, each its own colocated-scan groups, NCCL gradient all-reduce
+
+Multi-GPU: samples (colocated scan groups) are sharded by rank; the only collective is the bucketed gradient all-reduce
+(gcl_b200/sharding.py:FlatGradients -- one flat buffer, one NCCL AVG all-reduce) between backward and the SGD step.  BatchNorm statistics stay per rank, as with
+torch DDP without SyncBatchNorm (the reference trains on one GPU: no DistributedDataParallel anywhere in /lib).
 """
 import argparse
 import json
@@ -30,14 +36,21 @@ def main():
   import gcl_b200
   from gcl_b200 import MinkowskiEngine as ME, ops, synth
   from gcl_b200.loss import GroupContrastiveLoss, _exhaustive_hash
-  dev = torch.device("cuda:0")
+  import torch.distributed as dist
+  from gcl_b200.sharding import FlatGradients, gather_counts
+  rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+  local = int(os.environ.get("LOCAL_RANK", 0))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
   if args.tf32:
     ME.set_training_conv_algo("tf32")
   torch.manual_seed(0)
-  rng = np.random.RandomState(0)
+  rng = np.random.RandomState(rank)
   clouds = []
   for s in range(args.samples):
-    base = synth.cast(synth.Scene(40 + s), synth.NUSCENES, seed=s)
+    base = synth.cast(synth.Scene(40 + s + 100 * rank), synth.NUSCENES, seed=s + 100 * rank)
     for j in range(3):
       clouds.append((base + rng.normal(0, 0.01, base.shape)).astype(np.float32))
   xyz = torch.from_numpy(np.concatenate(clouds)).to(dev)
@@ -64,6 +77,7 @@ def main():
   index_hash = _exhaustive_hash(list(split), N)
   print(f"clouds={len(clouds)} voxels={N} groups={len(group)}", file=sys.stderr)
 
+  torch.manual_seed(0)  # identical initial weights on every rank
   model = gcl_b200.load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, conv1_kernel_size=5, normalize_feature=True).to(dev)
   model.train()
   opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
@@ -71,19 +85,24 @@ def main():
                               rng=np.random.RandomState(0))
   feats = torch.ones(N, 1, device=dev)
 
+  grads = FlatGradients(model.parameters())
+
   def step():
-    opt.zero_grad(set_to_none=True)
+    grads.zero()
     st = ME.SparseTensor(feats, coordinates=C)
     F = model(st).F
     pos, fin, neg = crit.finest_contrastive_loss(F, group, index, index_hash, finest, max_pos_cluster=256 * args.samples,
                                                  max_hn_samples=256 * args.samples)
     loss = pos + fin + neg
     loss.backward()
+    grads.allreduce()
     opt.step()
     return loss
 
-  for _ in range(2):
+  for _ in range(3):
     l0 = step()
+  if world > 1:
+    dist.barrier()
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
@@ -92,10 +111,23 @@ def main():
   e1.record()
   torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / args.steps
-  print(json.dumps({"metric": "gcl_train_step_ms", "value": round(ms, 2), "unit": "ms/step", "clouds": len(clouds), "voxels": N,
-                    "groups": int(len(group)), "loss_first": round(float(l0), 4), "loss_last": round(float(l), 4),
+  if world > 1:
+    tot_clouds, ms = gather_counts(float(len(clouds)), ms)
+    # every rank starts from the same seeded weights and applies the same averaged gradient: weights must stay identical
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    lo, hi = w.clone(), w.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks diverged after the gradient all-reduce"
+  else:
+    tot_clouds = len(clouds)
+  if rank == 0:
+    print(json.dumps({"metric": "gcl_train_step_ms", "value": round(ms, 2), "unit": "ms/step", "n_gpus": world,
+                    "scans_per_s": round(tot_clouds / ms * 1e3, 1), "clouds_per_rank": len(clouds), "voxels_rank0": N,
+                    "groups_rank0": int(len(group)), "loss_first": round(float(l0), 4), "loss_last": round(float(l), 4),
                     "conv_kernels": ("tcgen05 kind::tf32 fwd + dgrad, fp32 wgrad" if args.tf32 else
                                      "exact-fp32 CUDA-core fwd/dgrad/wgrad")}))
+  if world > 1:
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
