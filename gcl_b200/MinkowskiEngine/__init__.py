@@ -244,6 +244,7 @@ class _SparseConvFn(torch.autograd.Function):
   def forward(ctx, x, W, nbr_fwd, nbr_bwd, n_out, mirror, tc_fwd, tc_bwd):
     ctx.save_for_backward(x, W)
     ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.n_in, ctx.tc_bwd = nbr_fwd, nbr_bwd, mirror, x.shape[0], tc_bwd
+    ctx.tc_fwd = tc_fwd
     xc = x.contiguous()
     if tc_fwd is not None:
       Wt = ops.weights_to_tc(W.detach())
@@ -272,7 +273,15 @@ class _SparseConvFn(torch.autograd.Function):
       else:
         gx = ops.spconv_fwd(gout, Wd, ctx.nbr_bwd, ctx.n_in)
     if ctx.needs_input_grad[1]:
-      gW = ops.spconv_wgrad(x, gout, ctx.nbr_fwd, W3.shape[0]).view_as(W)
+      if ctx.tc_fwd is not None and ops.wgrad_tc_supported(x.shape[1], gout.shape[1]):
+        if ctx.tc_fwd == "mm":
+          gW = ops.spconv_wgrad_tc(x, gout, None, 1)
+        else:
+          srt, perm, mask = ctx.tc_fwd
+          gW = ops.spconv_wgrad_tc(x, gout, srt, W3.shape[0], row_perm=perm, tile_mask=mask)
+        gW = gW.view_as(W)
+      else:
+        gW = ops.spconv_wgrad(x, gout, ctx.nbr_fwd, W3.shape[0]).view_as(W)
     return gx, gW, None, None, None, None, None, None
 
 

@@ -115,5 +115,6 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
 }
 // host: 2-D fp32 tensor map over a row-major [n, c] matrix, box = 1 row x 32 channels, SWIZZLE_128B  (tma.cu)
 int make_rows_tensor_map(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows);
+int make_rows_tensor_map_sw(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows, bool atom32);
 
 }  // namespace gclb

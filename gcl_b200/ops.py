@@ -272,6 +272,23 @@ def spconv_wgrad(x: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor
   return gW
 
 
+def wgrad_tc_supported(cin: int, cout: int) -> bool:
+  return cin % 32 == 0 and cout % 32 == 0 and 32 <= cin <= 256 and 32 <= cout <= 256
+
+
+def spconv_wgrad_tc(x: torch.Tensor, gout: torch.Tensor, nbr_sorted: Optional[torch.Tensor], K: int,
+                    row_perm: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """Weight gradient on tcgen05 (tf32 operands) over the row-bucketed forward table; see gclb_spconv_wgrad_tc."""
+  require_cuda(x, gout, nbr_sorted, row_perm, tile_mask)
+  cin, cout = x.shape[1], gout.shape[1]
+  if nbr_sorted is not None:
+    assert nbr_sorted.dtype == torch.int32 and tuple(nbr_sorted.shape) == (gout.shape[0], K)
+  gW = torch.zeros((K, cin, cout), dtype=torch.float32, device=x.device)
+  call("gclb_spconv_wgrad_tc", ptr(x.contiguous()), cin, x.shape[0], ptr(gout.contiguous()), cout, gout.shape[0],
+       ptr(nbr_sorted), ptr(row_perm), ptr(tile_mask), K, ptr(gW), stream())
+  return gW
+
+
 def pointwise_tail(in0, in1, W1, W2, bias, normalize=True):
   n = in0.shape[0]
   c0, c1 = in0.shape[1], (in1.shape[1] if in1 is not None else 0)

@@ -169,6 +169,16 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
                       const int32_t* nbr, int32_t K, float* gW, void* stream);
+
+/* Same contraction on tcgen05 (kind::tf32 operands, fp32 accumulation in TMEM) over the row-bucketed table that
+ * gclb_kmap_sort_rows produced for the forward pass: nbr_sorted [n_out, K] (NULL = identity, K == 1), row_perm [n_out]
+ * (tile row -> output row, NULL = identity), tile_mask [ceil(n_out/128)] (NULL = walk every tile for every offset).
+ * Needs cin, cout in {32, 64, ..., 256}.  gW [K, cin, cout] is ACCUMULATED into (caller zeroes it); partial sums of
+ * different CTAs are merged with fp32 atomics, so the last bits depend on scheduling.
+ * Replaces: ME ConvolutionBackward (weight gradient) reached through loss.backward(), lib/colocation_trainer.py:879. */
+int gclb_spconv_wgrad_tc(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
+                         const int32_t* nbr_sorted, const int32_t* row_perm, const int32_t* tile_mask, int32_t K,
+                         float* gW, void* stream);
 /* pointwise tail of ResUNet: out = l2normalize( relu([in0|in1] W1) W2 + bias )   (model/resunet.py:217-230) */
 int gclb_pointwise_tail(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n, const float* W1,
                         int32_t cmid, const float* W2, const float* bias, int32_t cout, int32_t normalize,

@@ -455,6 +455,32 @@ def test_training_step_grads_vs_oracle(G, mode, w, tol):
     assert _rel(bg.float(), bo.float()) < (1e-5 if mode == "fp32" else tol), k
 
 
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 64), (32, 64), (128, 128), (256, 256), (256, 64), (64, 128), (128, 256),
+                                      (96, 64), (192, 32)])
+def test_wgrad_tc_vs_fp32(G, cin, cout):
+  """tcgen05 weight gradient (MN-major tf32 operands gathered by TMA) against the exact-fp32 CUDA-core kernel (itself
+  checked against oracle autograd above): stride-1 table, strided (down) table, and the K == 1 identity case."""
+  C_ref, _ = _oracle_voxelize([_random_cloud(51, 2500, 7.0), _random_cloud(52, 2300, 7.0)], 0.3)
+  cm = G.ops.hash_build(C_ref.to(G.dev))
+  g = torch.Generator().manual_seed(cin * 1000 + cout)
+  cm2 = G.ops.stride_map(cm, 2)
+  for name, cin_map, cout_map in [("s1", cm, cm), ("down", cm, cm2)]:
+    nbr, keys = G.ops.kernel_map(cin_map, cout_map, 3, with_keys=True)
+    srt, perm, mask = G.ops.kernel_map_sort(nbr, keys)
+    x = torch.randn(cin_map.n, cin, generator=g).to(G.dev)
+    go = torch.randn(cout_map.n, cout, generator=g).to(G.dev)
+    ref = G.ops.spconv_wgrad(x, go, nbr, 27)
+    got = G.ops.spconv_wgrad_tc(x, go, srt, 27, row_perm=perm, tile_mask=mask)
+    assert _rel(got, ref) < 3e-3, (name, _rel(got, ref))
+    got2 = G.ops.spconv_wgrad_tc(x, go, srt, 27, row_perm=perm, tile_mask=None)     # no masks: every tile, every offset
+    assert _rel(got2, ref) < 3e-3, (name, "nomask", _rel(got2, ref))
+  x = torch.randn(cm.n, cin, generator=g).to(G.dev)
+  go = torch.randn(cm.n, cout, generator=g).to(G.dev)
+  ref = (x.double().T @ go.double()).float()[None]
+  got = G.ops.spconv_wgrad_tc(x, go, None, 1)
+  assert _rel(got, ref) < 3e-3, ("mm", _rel(got, ref))
+
+
 # ----------------------------------------------------------------------------------------------- K4
 def _unit(n, c, seed):
   x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed))

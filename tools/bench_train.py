@@ -31,7 +31,7 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--samples", type=int, default=4)
   ap.add_argument("--voxel", type=float, default=0.3)
-  ap.add_argument("--tf32", action="store_true", help="forward + dgrad on the tcgen05 kind::tf32 kernel")
+  ap.add_argument("--tf32", action="store_true", help="forward, dgrad and wgrad on the tcgen05 kind::tf32 kernels")
   args = ap.parse_args()
   import gcl_b200
   from gcl_b200 import MinkowskiEngine as ME, ops, synth
@@ -124,7 +124,7 @@ def main():
     print(json.dumps({"metric": "gcl_train_step_ms", "value": round(ms, 2), "unit": "ms/step", "n_gpus": world,
                     "scans_per_s": round(tot_clouds / ms * 1e3, 1), "clouds_per_rank": len(clouds), "voxels_rank0": N,
                     "groups_rank0": int(len(group)), "loss_first": round(float(l0), 4), "loss_last": round(float(l), 4),
-                    "conv_kernels": ("tcgen05 kind::tf32 fwd + dgrad, fp32 wgrad" if args.tf32 else
+                    "conv_kernels": ("tcgen05 kind::tf32 fwd + dgrad + wgrad" if args.tf32 else
                                      "exact-fp32 CUDA-core fwd/dgrad/wgrad")}))
   if world > 1:
     dist.destroy_process_group()
