@@ -181,9 +181,11 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     K, cin, cout = W3.shape
     pairs = n_out if nbr is None else next(pair_counts[k] for k, v in tabs.items() if any(t is nbr for t in v))
-    alg_bytes = 4 * (in0.shape[0] * cin + n_out * cout) + 8 * pairs + 4 * K * cin * cout
+    # every tensor once at its storage width (fp16 between the 64..256-channel layers, fp32 elsewhere) + the map + weights
+    alg_bytes = (in0.element_size() * in0.shape[0] * cin + out.element_size() * n_out * cout + 8 * pairs
+                 + W.element_size() * K * cin * cout)
     if kw.get("residual") is not None:
-      alg_bytes += 4 * n_out * cout
+      alg_bytes += kw["residual"].element_size() * n_out * cout
     recs.append((e0, e1, alg_bytes, 2 * pairs * cin * cout))
     return out
 
@@ -344,11 +346,12 @@ def main():
   line = {"metric": "scan_pairs_per_sec", "value": round(value, 2), "unit": "pairs/s", "n_gpus": world,
           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-          "dtype": "tf32" if (lib.gclb_has_tcgen05() and args.algo != 1) else "f32", "data": "synthetic",
+          "dtype": "f16/tf32 operands, f32 accumulate" if (lib.gclb_has_tcgen05() and args.algo != 1) else "f32", "data": "synthetic",
           "mvoxels_per_sec": round(nvox / (ms * 1e-3) / 1e6, 3),
           "config": {"workload": workload, "pairs_per_step_per_gpu": args.pairs, "batches_in_flight": args.depth, "parallelism": f"pair-sharded x{world}, no collective",
                      "l2": f"inputs larger than L2: {n_batches} rotating batches, ~{step_ws_mb:.0f} MB algorithmic conv traffic per step vs 126 MB L2",
-                     "conv_algo": "tcgen05 kind::tf32" if (lib.gclb_has_tcgen05() and args.algo != 1) else "fp32 CUDA-core implicit GEMM"},
+                     "conv_algo": ("tcgen05: kind::f16 with fp16 activations for the 64..256-channel layers, kind::tf32 for the 32-channel stride-1 layers and the tail"
+                                   if (lib.gclb_has_tcgen05() and args.algo != 1) else "fp32 CUDA-core implicit GEMM")},
           "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(ms_e2e / args.steps, 3)},
           "gpu_launches": int(launches), "clocks": clk, "roofline": roof}

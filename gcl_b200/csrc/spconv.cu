@@ -377,19 +377,26 @@ using namespace gclb;
 
 extern "C" {
 
-int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
+int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, int64_t n_in, const void* W_,
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
-                    const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                    const float* scale, const float* shift, const void* residual_, int32_t relu, void* out_,
                     int64_t n_out, int32_t algo, void* stream) {
+  // fp32 unless flag bits 3 / 4 say fp16 (tcgen05 path); the kernels re-interpret
+  const float* in0 = static_cast<const float*>(in0_);
+  const float* in1 = static_cast<const float*>(in1_);
+  const float* W = static_cast<const float*>(W_);
+  const float* residual = static_cast<const float*>(residual_);
+  float* out = static_cast<float*>(out_);
   GCLB_CHECK_ARG(W && (n_out == 0 || out), "null pointer");
   GCLB_CHECK_ARG(c0 >= 1 && c1 >= 0 && K >= 1 && cout >= 1, "bad shape");
   GCLB_CHECK_ARG((c1 == 0) == (in1 == nullptr), "in1 / c1 mismatch");
   GCLB_CHECK_ARG(nbr || K == 1, "nbr may be NULL only for K == 1");
   GCLB_CHECK_ARG(n_in == 0 || in0, "null input");
   GCLB_CHECK_ARG(algo >= 0 && algo <= 2, "algo must be 0, 1 or 2");
-  GCLB_CHECK_ARG(relu >= 0 && relu <= 7,
-                 "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows, bit 2 = nbr is the re-ordered copy (tcgen05 path)");
-  GCLB_CHECK_ARG(algo == 2 || (relu & 6) == 0, "flag bits 1 and 2 exist on the tcgen05 path only");
+  GCLB_CHECK_ARG(relu >= 0 && relu <= 31,
+                 "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows, bit 2 = nbr is the re-ordered copy, bit 3 = fp16 "
+                 "inputs/residual/weights, bit 4 = fp16 output (bits 1-4: tcgen05 path)");
+  GCLB_CHECK_ARG(algo == 2 || (relu & 30) == 0, "flag bits 1-4 exist on the tcgen05 path only");
   GCLB_CHECK_ARG((relu & 4) == 0 || row_perm != nullptr, "flag bit 2 needs row_perm");
   GCLB_CHECK_ARG(row_perm == nullptr || (algo == 2 && nbr != nullptr), "row_perm is a tcgen05-path option and needs nbr");
   GCLB_CHECK_ARG(tile_mask == nullptr || (algo == 2 && nbr != nullptr && K <= 32), "tile_mask is a tcgen05-path option");

@@ -15,6 +15,8 @@
 //               overlapped with the next tile's main loop through a double-buffered TMEM accumulator.
 // Every output row is produced by exactly one CTA: no atomics, bit-reproducible.
 // All mbarrier waits are bounded spins that trap on a protocol bug instead of hanging the GPU.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace gclb {
@@ -46,7 +48,7 @@ struct TcShared {   // static shared: barriers + small per-tile metadata
   int act_k[4][32];
 };
 
-template <int COUT, int KVOL>
+template <int COUT, int KVOL, bool HALF>
 __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
                                                                       const __grid_constant__ CUtensorMap map0,
                                                                       const __grid_constant__ CUtensorMap map1) {
@@ -60,8 +62,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   int* nbr_buf = reinterpret_cast<int*>(smem_dyn + S * Cfg::STAGE);    // [NBUF][NBR_INTS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // HALF: activations (in0, in1, residual) are IEEE fp16 in HBM, weights an fp16 image, MMA kind::f16 -- a 128-byte
+  // operand row then holds 64 channels instead of 32: half the gather bytes, same 10-bit mantissa as kind::tf32
+  constexpr int KCH = HALF ? 64 : 32;
   const int cin = p.c0 + p.c1;
-  const int slabs = cin / KSLAB;
+  const int slabs = cin / KCH;
   const bool identity = (p.nbr == nullptr);     // K == 1 `mm` path: nbr[o] = o
   const bool nbr_sorted = (p.relu & 4) != 0;    // nbr is the physically re-ordered copy (else: read rows through perm)
 
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
       for (int i = 0; i < n_iter; ++i, ++it) {
         if ((int)(it % S) != warp) continue;              // successive rounds of a slot are ordered => no phase aliasing
         const int k = sh.act_k[b][i / slabs];
-        const int c = (i % slabs) * KSLAB;
+        const int c = (i % slabs) * KCH;
         const int stage = it % S;
         int r[4];
 #pragma unroll
@@ -116,7 +121,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
         const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
         if (lane == 0) {
           mbar_arrive_expect_tx(&sh.full[stage], A_BYTES + Cfg::B_BYTES);
-          bulk_g2s(a_s + A_BYTES, p.W + ((size_t)k * slabs + c / KSLAB) * (COUT * KSLAB), Cfg::B_BYTES, &sh.full[stage]);
+          bulk_g2s(a_s + A_BYTES, reinterpret_cast<const unsigned char*>(p.W) + ((size_t)k * slabs + c / KCH) * Cfg::B_BYTES,
+                   Cfg::B_BYTES, &sh.full[stage]);
         }
         __syncwarp();                                        // the barrier is armed before any gather can complete on it
         if (c < p.c0) tma_gather4(a_s + lane * 512, &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer (one thread) =======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(COUT);
+      constexpr uint32_t idesc = HALF ? make_idesc_f16(COUT) : make_idesc_tf32(COUT);
       uint32_t it = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -149,8 +155,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
           const uint32_t b_s = a_s + A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < KSLAB / 8; ++ks)    // 4 MMAs of K = 8 (32 bytes) inside the 128-byte swizzle row
-            umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {   // 4 MMAs of 32 bytes of K (8 tf32 / 16 fp16) inside the 128-byte swizzle row
+            if (HALF) umma_f16(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+            else umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+          }
           umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
         }
         if (n_iter > 0) umma_commit(&sh.acc_full[ab]);
@@ -230,10 +238,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
       int64_t o = p.n_out;                                   // rows past the end are never stored
       if (t_row < p.n_out) o = p.perm ? (int64_t)__ldg(p.perm + t_row) : t_row;
       const bool live = o < p.n_out;
-      const float* res = (p.residual && live) ? p.residual + (size_t)o * COUT : nullptr;
-      float4 rc[8];
+      // residual has the dtype of the inputs (it IS a block's input): 32 columns = 8 (fp32) or 4 (fp16) 16-byte loads
+      constexpr int RV = HALF ? 4 : 8;
+      constexpr int RES_B = HALF ? 2 : 4;
+      const unsigned char* res = (p.residual && live) ? reinterpret_cast<const unsigned char*>(p.residual) + (size_t)o * COUT * RES_B
+                                                       : nullptr;
+      const bool out_half = (p.relu & 16) != 0;
+      float4 rc[RV];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < RV; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait(&sh.acc_full[ab], (lt / NACC) & 1);
       tc_fence_after();
       const bool empty_tile = (*reinterpret_cast<volatile int*>(&sh.acc_n_act[ab]) == 0);
@@ -242,11 +255,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
       for (int n0 = 0; n0 < COUT; n0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)n0, v);
-        float4 rn[8];                                       // residual of the NEXT 32 columns, in flight during this chunk
+        float4 rn[RV];                                      // residual of the NEXT 32 columns, in flight during this chunk
         const bool more = (n0 + 32 < COUT);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          rn[q] = (more && res) ? __ldg(reinterpret_cast<const float4*>(res + n0 + 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < RV; ++q)
+          rn[q] = (more && res) ? __ldg(reinterpret_cast<const float4*>(res + (size_t)(n0 + 32) * RES_B) + q)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
         if (!more) {                                        // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
@@ -258,7 +272,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           for (int q = 0; q < 32; q += 4) {
             float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q)) : make_float4(1.f, 1.f, 1.f, 1.f);
             float4 sf = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 r = rc[q >> 2];
+            float4 r;
+            if constexpr (HALF) {   // 8 halves per 16-byte vector: columns q..q+3 are the low or high half of vector q / 8
+              const float4 raw = rc[q >> 3];
+              const uint32_t w0 = __float_as_uint((q & 4) ? raw.z : raw.x), w1 = __float_as_uint((q & 4) ? raw.w : raw.y);
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+              r = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              r = rc[q >> 2];
+            }
             y[q + 0] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 0]), sc.x, sf.x) + r.x;
             y[q + 1] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 1]), sc.y, sf.y) + r.y;
             y[q + 2] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 2]), sc.z, sf.z) + r.z;
@@ -276,12 +299,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
 #pragma unroll
             for (int q = 0; q < 32; ++q) y[q] = y[q] / nrm;
           }
-          float* dst = p.out + (size_t)o * COUT + n0;
+          if (out_half) {                               // fp16 activations for the next layer (saturating, round to nearest)
+            __half* dst = reinterpret_cast<__half*>(p.out) + (size_t)o * COUT + n0;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+            for (int q = 0; q < 32; q += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = fminf(fmaxf(y[q + 2 * j], -65504.f), 65504.f);
+                const float b = fminf(fmaxf(y[q + 2 * j + 1], -65504.f), 65504.f);
+                const __half2 h = __floats2half2_rn(a, b);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst + q) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(p.out) + (size_t)o * COUT + n0;
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+          }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) rc[q] = rn[q];
+        for (int q = 0; q < RV; ++q) rc[q] = rn[q];
       }
     }
   }
@@ -314,11 +353,28 @@ __global__ void __launch_bounds__(256) weights_to_tc_kernel(const float* __restr
   }
 }
 
-template <int COUT, int KVOL>
+// fp16 image: per (k, 64-channel slab) one cout x 128 B block (row n = 64 halves, 16-byte chunk j at (j ^ n%8)),
+// values rounded to nearest-even fp16 (saturating).
+__global__ void __launch_bounds__(256) weights_to_tc_f16_kernel(const float* __restrict__ W, int K, int cin, int cout,
+                                                                __half* __restrict__ Wimg) {
+  const int64_t total = (int64_t)K * cin * cout;
+  const int slabs = cin / 64;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(e % cout);
+    const int c = (int)((e / cout) % cin);
+    const int k = (int)(e / ((int64_t)cout * cin));
+    const int sl = c / 64, cc = c % 64, j = cc >> 3, w = cc & 7;
+    const int64_t blk = ((int64_t)k * slabs + sl) * ((int64_t)cout * 64);
+    const int off = (n >> 3) * 512 + (n & 7) * 64 + ((j ^ (n & 7)) << 3) + w;     // in halves
+    Wimg[blk + off] = __float2half_rn(fminf(fmaxf(W[e], -65504.f), 65504.f));
+  }
+}
+
+template <int COUT, int KVOL, bool HALF>
 static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   using Cfg = TcCfg<COUT>;
   size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
-  auto kern = spconv_fwd_tc_kernel<COUT, KVOL>;
+  auto kern = spconv_fwd_tc_kernel<COUT, KVOL, HALF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -327,8 +383,8 @@ static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   const int num_tiles = (int)((p.n_out + TM - 1) / TM);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;     // persistent: one CTA per SM
   CUtensorMap map0, map1;
-  int rc = make_rows_tensor_map(&map0, p.in0, n_in, p.c0, 1);
-  if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map(&map1, p.in1, n_in, p.c1, 1) : (map1 = map0, GCLB_OK);
+  int rc = make_rows_tensor_map_ex(&map0, p.in0, n_in, p.c0, HALF, false);
+  if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, HALF, false) : (map1 = map0, GCLB_OK);
   if (rc != GCLB_OK) return rc;
   kern<<<grid, kTcThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
   e = cudaGetLastError();
@@ -342,7 +398,9 @@ static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
 
 bool spconv_tc_supported(const ConvParams& p) {
   const int cin = p.c0 + p.c1;
-  if (p.c0 % KSLAB != 0 || p.c1 % KSLAB != 0 || cin < KSLAB) return false;
+  const int kch = (p.relu & 8) ? 64 : KSLAB;     // fp16 operands: 64 channels per 128-byte row
+  if (p.c0 % kch != 0 || p.c1 % kch != 0 || cin < kch) return false;
+  if ((p.relu & 16) && ((p.relu >> 1) & 1)) return false;   // the fused L2 normalise writes fp32 descriptors
   if (!(p.cout == 32 || p.cout == 64 || p.cout == 128 || p.cout == 256)) return false;
   if (!(p.K == 27 || p.K == 1)) return false;
   if (((p.relu >> 1) & 1) && p.cout != 32) return false;   // fused L2 normalise needs the whole row in one TMEM read
@@ -350,9 +408,10 @@ bool spconv_tc_supported(const ConvParams& p) {
 }
 
 int spconv_fwd_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
-#define GCLB_TC_CASE(C) \
-  case C:               \
-    return p.K == 27 ? launch_tc<C, 27>(p, n_in, st) : launch_tc<C, 1>(p, n_in, st);
+#define GCLB_TC_CASE(C)                                                                                \
+  case C:                                                                                              \
+    if (p.relu & 8) return p.K == 27 ? launch_tc<C, 27, true>(p, n_in, st) : launch_tc<C, 1, true>(p, n_in, st); \
+    return p.K == 27 ? launch_tc<C, 27, false>(p, n_in, st) : launch_tc<C, 1, false>(p, n_in, st);
   switch (p.cout) {
     GCLB_TC_CASE(32)
     GCLB_TC_CASE(64)
@@ -378,6 +437,18 @@ int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, flo
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   weights_to_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, Wt);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, void* Wt, void* stream) {
+  GCLB_CHECK_ARG(W && Wt && K >= 1 && cin >= 1 && cout >= 1, "bad arguments");
+  GCLB_CHECK_ARG(cin % 64 == 0 && cout % 8 == 0, "fp16 tensor-core image needs cin % 64 == 0 and cout % 8 == 0");
+  int64_t total = (int64_t)K * cin * cout;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  weights_to_tc_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, reinterpret_cast<__half*>(Wt));
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -78,6 +78,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
+// D = F32, A = B = F16 (format 0), both K-major, M = 128, N = n   (K = 16 per instruction)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -116,5 +128,7 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
 // host: 2-D fp32 tensor map over a row-major [n, c] matrix, box = 1 row x 32 channels, SWIZZLE_128B  (tma.cu)
 int make_rows_tensor_map(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows);
 int make_rows_tensor_map_sw(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows, bool atom32);
+// general form: rows of fp32 (box = 32 channels) or fp16 (box = 64 channels), 128 bytes per box row either way
+int make_rows_tensor_map_ex(CUtensorMap* map, const void* base, int64_t n, int c, bool half, bool atom32);
 
 }  // namespace gclb

@@ -25,6 +25,9 @@ constexpr int kWgMmaWarp = 8;
 constexpr int kWgThreads = 13 * 32;
 constexpr int kWgMaxTiles = 2048;     // active tiles one CTA can list
 
+// 3x3x3 offsets (index = (dx+1) + 3(dy+1) + 9(dz+1), the table's column order) sorted by |d|_1: centre, 6 faces, 12 edges, 8 corners
+__constant__ int kPopularity27[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+
 struct WgShared {
   uint64_t full[8], empty[8];
   uint64_t acc_full;
@@ -60,7 +63,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) spconv_wgrad_tc_kernel(WgParams
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ WgShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k = blockIdx.x % p.K, part = blockIdx.x / p.K;
+  // items are handed out in blockIdx order: start the heavy offsets first (centre, then faces, edges, corners of the
+  // 3x3x3 stencil -- populated in that order of frequency) so the light ones fill the tail
+  int k = blockIdx.x % p.K;
+  int part = blockIdx.x / p.K;
+  if (p.K == 27) {
+    part = blockIdx.x % p.P;
+    k = blockIdx.x / p.P;   // all parts of one offset are adjacent, offsets in popularity order
+    k = kPopularity27[k];
+  }
   const int S = p.stages;
   const int rows = p.rows, chunks = TM / rows, quads = rows / 4;
   const int slabsA = p.cin / 32, slabsB = p.cout / 32;

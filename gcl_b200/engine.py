@@ -54,9 +54,14 @@ class _Tables:
 class ResUNetEngine:
   """Build from any ResUNet2-family module (reference class or gcl_b200.resunet) holding the trained weights."""
 
-  def __init__(self, model, device="cuda", algo: int = 0):
+  def __init__(self, model, device="cuda", algo: int = 0, half: bool = True):
+    """algo: 0 = tcgen05 kernels where a layer qualifies, 1 = exact-fp32 CUDA-core kernels everywhere.
+    half: store the activations of every layer whose input channels are a multiple of 64 as fp16 and run it with
+    kind::f16 (fp32 accumulation): same 10-bit mantissa as the kind::tf32 operands but rounded to nearest instead of
+    truncated (measured closer to exact fp32 than tf32: tools/precision_study.py), and half the gather bytes."""
     self.device = torch.device(device)
     self.algo = algo
+    self.half = bool(half) and algo != 1
     self.normalize = bool(model.normalize_feature)
     d = self.device
     self.conv1_ks = model.conv1.kernel_size
@@ -78,6 +83,7 @@ class ResUNetEngine:
 
     # tensor-core weight copies ([K, Cout, Cin], tf32-rounded) for every layer the tcgen05 kernel covers
     self.tc = {}
+    self.tc16 = {}         # fp16 images of the layers that run with fp16 activations
     self.tail_tc = None
     self.sort_rows = True
     self._side = None      # side streams for overlapped kernel-map construction
@@ -89,6 +95,8 @@ class ResUNetEngine:
         c0 = self.SPLIT.get(key, cin)
         if ops.tc_supported(c0, cin - c0, cout, K):
           self.tc[key] = ops.weights_to_tc(W)
+        if self.half and ops.tc_supported(c0, cin - c0, cout, K, half=True):
+          self.tc16[key] = ops.weights_to_tc(W, half=True)
       # pointwise tail on the tensor cores: [y1 | s1] W1 -> ReLU -> W2 + bias -> L2 normalise (fused in the epilogue)
       c_s1 = type(model).CHANNELS[1]
       c_y1 = self.W1.shape[0] - c_s1
@@ -101,24 +109,36 @@ class ResUNetEngine:
   SPLIT = {}
 
   # ---- building blocks
-  def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False):
+  def _want(self, key):
+    """storage dtype a layer reads its inputs in"""
+    return torch.float16 if key in self.tc16 else torch.float32
+
+  def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False, out_dtype=torch.float32):
     W, sc, sh = self.p[key]
+    dt = self._want(key)
+    # no-ops on the tuned path (every producer already writes what its consumer reads); a model variant whose channel
+    # widths mix eligible and ineligible layers converts here
+    x = x if x.dtype == dt else x.to(dt)
+    x2 = x2 if (x2 is None or x2.dtype == dt) else x2.to(dt)
+    residual = residual if (residual is None or residual.dtype == dt) else residual.to(dt)
     if key in self.tc:
       perm = mask = None
       is_sorted = True
       if isinstance(nbr, tuple):          # (table, sorted copy or None, perm, tile masks) from build_maps
         table, srt, perm, mask = nbr
         nbr, is_sorted = (srt, True) if srt is not None else (table, False)
-      return ops.spconv_fwd(x, self.tc[key], nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
-                            algo=2, row_perm=perm, tile_mask=mask, nbr_is_sorted=is_sorted)
+      Wimg = self.tc16[key] if dt == torch.float16 else self.tc[key]
+      return ops.spconv_fwd(x, Wimg, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
+                            algo=2, row_perm=perm, tile_mask=mask, nbr_is_sorted=is_sorted, out_dtype=out_dtype)
     if isinstance(nbr, tuple):
       nbr = nbr[0]
-    return ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)
+    y = ops.spconv_fwd(x, W, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu, algo=1)
+    return y if out_dtype == torch.float32 else y.to(out_dtype)
 
-  def _block(self, name, x, nbr):
+  def _block(self, name, x, nbr, out_dtype=torch.float32):
     n = x.shape[0]
-    t = self._conv(name + ".1", x, nbr, n, relu=True)
-    return self._conv(name + ".2", t, nbr, n, residual=x, relu=True)
+    t = self._conv(name + ".1", x, nbr, n, relu=True, out_dtype=self._want(name + ".2"))
+    return self._conv(name + ".2", t, nbr, n, residual=x, relu=True, out_dtype=out_dtype)
 
   # order in which forward() first touches each table
   TABLE_ORDER = ("c1", "k3s1", "down1", "k3s2", "down2", "k3s4", "down4", "k3s8", "up4", "up2", "up1")
@@ -198,14 +218,20 @@ class ResUNetEngine:
       W, sc, sh = self.p["conv1"]
       c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
     else:
-      c1 = self._conv("conv1", x, km["c1"] if self.conv1_ks != 1 else None, n1)
-    s1 = self._block("block1", c1, km["k3s1"])
-    s2 = self._block("block2", self._conv("conv2", s1, km["down1"], n2), km["k3s2"])
-    s4 = self._block("block3", self._conv("conv3", s2, km["down2"], n4), km["k3s4"])
-    s8 = self._block("block4", self._conv("conv4", s4, km["down4"], n8), km["k3s8"])
-    y4 = self._block("block4_tr", self._conv("conv4_tr", s8, km["up4"], n4), km["k3s4"])
-    y2 = self._block("block3_tr", self._conv("conv3_tr", y4, km["up2"], n2, x2=s4), km["k3s2"])
-    y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2), km["k3s1"])
+      c1 = self._conv("conv1", x, km["c1"] if self.conv1_ks != 1 else None, n1, out_dtype=self._want("block1.1"))
+    # every layer writes the storage dtype its consumer reads (fp16 between the 64..256-channel layers, fp32 at the
+    # 32-channel stride-1 level and for the descriptors), converting in its epilogue
+    w = self._want
+    s1 = self._block("block1", c1, km["k3s1"], out_dtype=w("conv2"))
+    s2 = self._block("block2", self._conv("conv2", s1, km["down1"], n2, out_dtype=w("block2.1")), km["k3s2"], w("conv3"))
+    s4 = self._block("block3", self._conv("conv3", s2, km["down2"], n4, out_dtype=w("block3.1")), km["k3s4"], w("conv4"))
+    s8 = self._block("block4", self._conv("conv4", s4, km["down4"], n8, out_dtype=w("block4.1")), km["k3s8"], w("conv4_tr"))
+    y4 = self._block("block4_tr", self._conv("conv4_tr", s8, km["up4"], n4, out_dtype=w("block4_tr.1")), km["k3s4"],
+                     w("conv3_tr"))
+    y2 = self._block("block3_tr", self._conv("conv3_tr", y4, km["up2"], n2, x2=s4, out_dtype=w("block3_tr.1")), km["k3s2"],
+                     w("conv2_tr"))
+    y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2, out_dtype=w("block2_tr.1")), km["k3s1"])
+    s1 = s1 if s1.dtype == torch.float32 else s1.float()     # the pointwise tail reads fp32
     if getattr(self, "tail_tc", None) is not None:
       h = ops.spconv_fwd(y1, self.tail_tc[0], None, n1, in1=s1, relu=True, algo=2)
       return ops.spconv_fwd(h, self.tail_tc[1], None, n1, shift=self.bias, normalize=self.normalize, algo=2)

@@ -210,9 +210,10 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
                out: Optional[torch.Tensor] = None, algo: int = 0, normalize: bool = False,
                row_perm: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None,
-               nbr_is_sorted: bool = True) -> torch.Tensor:
+               nbr_is_sorted: bool = True, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
   """K3 forward.  W is [K, Cin, Cout] (or [Cin, Cout] for the K == 1 `mm` path); with algo=2 (tcgen05) W is the
-  tensor-core layout [K, Cout, Cin] from `weights_to_tc`."""
+  tensor-core layout [K, Cout, Cin] from `weights_to_tc`.  fp16 activations (algo=2): pass float16 in0 / in1 / residual
+  with a float16 weight image (`weights_to_tc(W, half=True)`); out_dtype picks the output storage (default: in0's)."""
   require_cuda(in0, W, nbr, in1, scale, shift, residual)
   if W.dim() == 2:
     W = W.unsqueeze(0)
@@ -223,12 +224,17 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   c0 = in0.shape[1]
   c1 = in1.shape[1] if in1 is not None else 0
   assert c0 + c1 == cin, f"channel mismatch: {c0}+{c1} vs {cin}"
-  assert in0.dtype == torch.float32 and W.dtype == torch.float32
+  half = in0.dtype == torch.float16
+  assert in0.dtype in (torch.float32, torch.float16) and W.dtype == in0.dtype, (in0.dtype, W.dtype)
+  assert (in1 is None or in1.dtype == in0.dtype) and (residual is None or residual.dtype == in0.dtype)
+  assert not half or algo == 2, "fp16 activations exist on the tcgen05 path only"
   if nbr is not None:
     assert nbr.dtype == torch.int32 and tuple(nbr.shape) == (n_out, K)
   if out is None:
-    out = torch.empty((n_out, cout), dtype=torch.float32, device=in0.device)
+    out = torch.empty((n_out, cout), dtype=out_dtype or in0.dtype, device=in0.device)
+  assert out.dtype in (torch.float32, torch.float16) and (algo == 2 or out.dtype == torch.float32)
   flags = int(bool(relu)) | (2 if normalize else 0) | (4 if (row_perm is not None and nbr_is_sorted) else 0)
+  flags |= (8 if half else 0) | (16 if out.dtype == torch.float16 else 0)
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
        ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), flags, ptr(out), n_out, algo, stream())
   return out
@@ -248,19 +254,20 @@ def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int,
   return out
 
 
-def weights_to_tc(W: torch.Tensor) -> torch.Tensor:
+def weights_to_tc(W: torch.Tensor, half: bool = False) -> torch.Tensor:
   """[K, Cin, Cout] (or [Cin, Cout]) -> tensor-core image (shape [K, Cout, Cin], pre-swizzled per 32-channel slab,
-  rounded to tf32); done once per layer."""
+  rounded to tf32; half=True: per 64-channel slab, rounded to fp16); done once per layer."""
   require_cuda(W)
   W3 = (W if W.dim() == 3 else W.unsqueeze(0)).contiguous().float()
   K, cin, cout = W3.shape
-  Wt = torch.empty((K, cout, cin), dtype=torch.float32, device=W.device)
-  call("gclb_weights_to_tc", ptr(W3), K, cin, cout, ptr(Wt), stream())
+  Wt = torch.empty((K, cout, cin), dtype=torch.float16 if half else torch.float32, device=W.device)
+  call("gclb_weights_to_tc_f16" if half else "gclb_weights_to_tc", ptr(W3), K, cin, cout, ptr(Wt), stream())
   return Wt
 
 
-def tc_supported(c0: int, c1: int, cout: int, K: int) -> bool:
-  return (_lib.load().gclb_has_tcgen05() == 1 and c0 % 32 == 0 and c1 % 32 == 0 and c0 >= 32
+def tc_supported(c0: int, c1: int, cout: int, K: int, half: bool = False) -> bool:
+  kch = 64 if half else 32
+  return (_lib.load().gclb_has_tcgen05() == 1 and c0 % kch == 0 and c1 % kch == 0 and c0 >= kch
           and cout in (32, 64, 128, 256) and K in (1, 27))
 
 

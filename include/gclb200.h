@@ -150,14 +150,23 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
  *         2   = tcgen05 kind::tf32 tensor-core kernel, fp32 accumulate in TMEM.  W must then be in the tensor-core
  *               image produced by gclb_weights_to_tc; needs c0 % 32 == 0, c1 % 32 == 0,
  *               cout in {32, 64, 128, 256}, K <= 27 (otherwise GCLB_ERR_UNSUPPORTED).
+ *   fp16 activations (tcgen05 path, flags): bit 3 (8) = in0, in1 and residual are IEEE fp16 [n, c] and W is the fp16
+ *               image from gclb_weights_to_tc_f16; the MMA is kind::f16 (fp32 accumulate; fp16 has the 10-bit mantissa
+ *               of tf32 but is rounded to nearest when stored, so it is the MORE accurate of the two -- see
+ *               tools/precision_study.py) and a gathered 128-byte row carries 64 channels instead of 32: needs
+ *               c0 % 64 == 0, c1 % 64 == 0.  bit 4 (16) = `out` is fp16 (saturating round-to-nearest), independent of
+ *               bit 3, so a layer can convert in either direction.  scale/shift are always fp32.
  * ---------------------------------------------------------------------------------------------------- */
 /* W [K, cin, cout] (ME layout) -> tensor-core image of the same size: per (k, 32-channel slab) one contiguous
  * cout x 128 B block laid out exactly like the SWIZZLE_128B K-major shared-memory tile, values rounded to nearest tf32
  * (done once per layer; needs cin % 32 == 0, cout % 8 == 0) */
 int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream);
-int gclb_spconv_fwd(const float* in0, int32_t c0, const float* in1, int32_t c1, int64_t n_in, const float* W,
+/* same for the fp16 path: per (k, 64-channel slab) one cout x 128 B block of fp16 (round to nearest); Wt holds
+ * K*cin*cout halves; needs cin % 64 == 0, cout % 8 == 0 */
+int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, void* Wt, void* stream);
+int gclb_spconv_fwd(const void* in0, int32_t c0, const void* in1, int32_t c1, int64_t n_in, const void* W,
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
-                    const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                    const float* scale, const float* shift, const void* residual, int32_t relu_flags, void* out,
                     int64_t n_out, int32_t algo, void* stream);
 /* stride-1 convolution with a small input width (cin <= 4, e.g. conv1 of ResUNet: cin = 1, kernel 5^3) with the kernel
  * map FUSED into the convolution: the kernel probes the coordinate hash of the (single) coordinate map itself, so no

@@ -303,6 +303,49 @@ def test_tc_two_source_epilogue(G):
   assert _rel(got, ref) < FEAT_TOL
 
 
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 64), (256, 256), (64, 32), (128, 128)])
+def test_tc_fp16_activations(G, cin, cout):
+  """kind::f16 path: fp16 activations / residual / weight image, fp32 accumulation, fp32 or fp16 output.
+  (a) small integers are exact in fp16: bit-exact against integer arithmetic (pins the 64-channel row layout, the fp16
+  weight image, the residual decode and both output stores);  (b) random data against the oracle convolution of the
+  fp16-rounded operands (products of two fp16 values are exact in fp32, so only the summation order differs)."""
+  torch.manual_seed(cin + cout)
+  C_ref, _ = _oracle_voxelize([_random_cloud(24, 4000, 9.0)], 0.3)
+  n = len(C_ref)
+  nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(3, 1))
+  nbr_d = torch.from_numpy(nbr).int().to(G.dev)
+  srt, perm, mask = G.ops.kernel_map_sort(nbr_d)
+  c0 = cin // 2 if cin >= 128 else cin                          # two-source gather for the wide cases
+  xi = torch.randint(-2, 3, (n, cin)).float()
+  Wi = torch.randint(-2, 3, (27, cin, cout)).float()
+  ri = torch.randint(-2, 3, (n, cout)).float()
+  ref = torch.relu(OME.sparse_conv_reference(xi, Wi, nbr, n) + ri)
+  Wh = G.ops.weights_to_tc(Wi.to(G.dev), half=True)
+  a = xi[:, :c0].contiguous().half().to(G.dev)
+  b = xi[:, c0:].contiguous().half().to(G.dev) if c0 < cin else None
+  for out_dtype in (torch.float32, torch.float16):
+    got = G.ops.spconv_fwd(a, Wh, srt, n, in1=b, residual=ri.half().to(G.dev), relu=True, algo=2, row_perm=perm,
+                           tile_mask=mask, out_dtype=out_dtype)
+    assert got.dtype == out_dtype and torch.equal(got.float().cpu(), ref)       # |values| < 2048: exact in fp16 too
+  x = torch.randn(n, cin)
+  W = torch.randn(27, cin, cout) / np.sqrt(27 * cin)
+  sc, sh = torch.rand(cout) + 0.5, torch.randn(cout)
+  ref = OME.sparse_conv_reference(x.half().float(), W.half().float(), nbr, n) * sc + sh
+  got = G.ops.spconv_fwd(x.half().to(G.dev), G.ops.weights_to_tc(W.to(G.dev), half=True), nbr_d, n, scale=sc.to(G.dev),
+                         shift=sh.to(G.dev), algo=2, out_dtype=torch.float32)
+  assert _rel(got, ref) < 1e-5
+  # against the UNROUNDED operands: the storage precision itself, same bar as the tf32 path
+  assert _rel(got, OME.sparse_conv_reference(x, W, nbr, n) * sc + sh) < FEAT_TOL
+  # fp32 -> fp16 converting layer (tf32 kernel writing fp16) and the K == 1 dense path with fp16 operands
+  g32 = G.ops.spconv_fwd(x.to(G.dev), G.ops.weights_to_tc(W.to(G.dev)), nbr_d, n, algo=2)
+  g16 = G.ops.spconv_fwd(x.to(G.dev), G.ops.weights_to_tc(W.to(G.dev)), nbr_d, n, algo=2, out_dtype=torch.float16)
+  assert g16.dtype == torch.float16 and torch.equal(g16, g32.half())
+  W1 = torch.randint(-3, 4, (1, cin, cout)).float()
+  got = G.ops.spconv_fwd(xi.half().to(G.dev), G.ops.weights_to_tc(W1.to(G.dev), half=True), None, n, algo=2,
+                         out_dtype=torch.float32)
+  assert torch.equal(got.cpu(), xi @ W1[0])
+
+
 def test_spconv_two_source_and_pointwise(G):
   torch.manual_seed(5)
   C_ref, _ = _oracle_voxelize([_random_cloud(22, 2000, 6.0)], 0.3)
