@@ -168,6 +168,7 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
   cm1, _ = ops.voxelize(xyz_dev, VOXEL, ptr)
   maps = eng.build_maps(cm1)
   cms, km = maps
+  eng.forward(cm1, torch.ones((cm1.n, 1), device=xyz_dev.device), maps)   # conv1 adds the stride-1 3x3x3 table it emits
   tabs = {k: (v if isinstance(v, tuple) else (v,)) for k, v in km.items()}
   pair_counts = {k: int((v[0] >= 0).sum().item()) for k, v in tabs.items()}
   recs = []

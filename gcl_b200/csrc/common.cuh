@@ -115,6 +115,26 @@ __device__ __forceinline__ int hash_find(const HashTable& t, uint64_t key) {
   return -1;
 }
 
+// per-offset constants of a lane: coordinate deltas, the same deltas as ONE 64-bit addend of the packed key
+// (fields are biased, so base + delta is the packed key of the neighbour as long as no field leaves its 18 bits), and
+// the direction bits of the row key
+struct LaneOffset {
+  int dx, dy, dz;
+  long long dkey;
+  int dirbits;
+};
+__device__ __forceinline__ LaneOffset lane_offset(int k, int ksize, int half, int scale) {
+  LaneOffset f;
+  const int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
+  f.dx = (ix - half) * scale;
+  f.dy = (iy - half) * scale;
+  f.dz = (iz - half) * scale;
+  f.dkey = (long long)f.dx * (1ll << 36) + (long long)f.dy * (1ll << 18) + (long long)f.dz;
+  f.dirbits = (ix < half ? 1 : 0) | (ix > half ? 2 : 0) | (iy < half ? 4 : 0) | (iy > half ? 8 : 0) | (iz < half ? 16 : 0) |
+              (iz > half ? 32 : 0);
+  return f;
+}
+
 __device__ __forceinline__ int floor_div(int a, int s) { return (a >= 0) ? a / s : -((-a + s - 1) / s); }
 
 // ---- ordered stream compaction of N flags (3 tiny launches, deterministic) -------------------------------

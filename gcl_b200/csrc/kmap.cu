@@ -17,39 +17,41 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int half = (ksize & 1) ? ksize / 2 : 0;
+  const int reach = (ksize - 1) * step;                 // |delta| never exceeds this on any axis
+  const int amask = in_stride > 1 ? in_stride - 1 : 0;  // tensor strides are powers of two
+  // the first 32 offsets (all of a 3x3x3 map) never change: keep their deltas in registers, no div/mod per row
+  const LaneOffset f0 = lane_offset(lane < K ? lane : 0, ksize, half, sign * step);
   const int64_t o0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int64_t ostep = (int64_t)gridDim.x * warps_per_block;
   int4 c_next = o0 < n_out ? __ldg(reinterpret_cast<const int4*>(out_c4) + o0) : make_int4(0, 0, 0, 0);
   for (int64_t o = o0; o < n_out; o += ostep) {
     const int4 c = c_next;                       // software pipeline: the next row's coordinates are already in flight
     if (o + ostep < n_out) c_next = __ldg(reinterpret_cast<const int4*>(out_c4) + o + ostep);
+    // every neighbour of this row keeps its packed fields in range => neighbour key = base key + per-lane constant
+    const int lim = kAxisBias - reach;
+    const bool safe = (unsigned)c.x < 1023u && c.y >= -lim && c.y < lim && c.z >= -lim && c.z < lim && c.w >= -lim && c.w < lim;
+    const uint64_t base = safe ? pack_key(c.x, c.y, c.z, c.w) : 0ull;
     int key = 0;
     unsigned rmask = 0;
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
-      int r = -1, ix = 0, iy = 0, iz = 0;
+      const LaneOffset f = (k0 == 0) ? f0 : lane_offset(k < K ? k : 0, ksize, half, sign * step);
+      int r = -1;
       if (k < K) {
-        ix = k % ksize; iy = (k / ksize) % ksize; iz = k / (ksize * ksize);
-        int x = c.y + sign * (ix - half) * step;
-        int y = c.z + sign * (iy - half) * step;
-        int z = c.w + sign * (iz - half) * step;
+        const int x = c.y + f.dx, y = c.z + f.dy, z = c.w + f.dz;
         // rows of the probed map sit on multiples of ITS tensor stride: a misaligned candidate (19 of the 27 offsets of
         // every fine voxel of a transposed map) cannot exist and is rejected without touching the table
-        const bool aligned = in_stride <= 1 || ((x % in_stride) == 0 && (y % in_stride) == 0 && (z % in_stride) == 0);
-        r = (aligned && coord_in_range(c.x, x, y, z)) ? hash_find(t, pack_key(c.x, x, y, z)) : -1;
+        const bool aligned = ((x | y | z) & amask) == 0;
+        if (aligned) {
+          if (safe) r = hash_find(t, base + (uint64_t)f.dkey);
+          else if (coord_in_range(c.x, x, y, z)) r = hash_find(t, pack_key(c.x, x, y, z));
+        }
         nbr[o * K + k] = r;
         if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
       }
       if (row_masks && k0 == 0) rmask = __ballot_sync(0xffffffffu, r >= 0);   // populated offsets of this row (K <= 32)
-      if (row_keys) {   // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
-        const bool v = r >= 0;
-        key |= __ballot_sync(0xffffffffu, v && ix < half) ? 1 : 0;
-        key |= __ballot_sync(0xffffffffu, v && ix > half) ? 2 : 0;
-        key |= __ballot_sync(0xffffffffu, v && iy < half) ? 4 : 0;
-        key |= __ballot_sync(0xffffffffu, v && iy > half) ? 8 : 0;
-        key |= __ballot_sync(0xffffffffu, v && iz < half) ? 16 : 0;
-        key |= __ballot_sync(0xffffffffu, v && iz > half) ? 32 : 0;
-      }
+      // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
+      if (row_keys) key |= (int)__reduce_or_sync(0xffffffffu, (unsigned)(r >= 0 ? f.dirbits : 0));
     }
     if (row_keys && lane == 0) {
       row_keys[o] = (uint8_t)key;
@@ -233,7 +235,7 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   GCLB_CHECK_ARG(row_masks == nullptr || ksize * ksize * ksize <= 32, "row masks need ksize^3 <= 32");
   GCLB_CHECK_ARG(key_hist == nullptr || row_keys != nullptr, "key_hist needs row_keys");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1) &&
-                     in_tensor_stride >= 0,
+                     in_tensor_stride >= 0 && (in_tensor_stride & (in_tensor_stride - 1)) == 0,
                  "bad kernel geometry");
   if (n_out == 0) return GCLB_OK;
   int K = ksize * ksize * ksize;

@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(256) spconv_fwd_small_cin_kernel(ConvParams p)
 template <int CIN>
 __global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvParams p, HashTable t,
                                                                           const int32_t* __restrict__ coords4, int ksize,
-                                                                          int step) {
+                                                                          int step, int32_t* __restrict__ nbr3,
+                                                                          uint8_t* __restrict__ row_keys,
+                                                                          uint32_t* __restrict__ row_masks,
+                                                                          int32_t* __restrict__ key_hist, int64_t hist_blocks) {
   extern __shared__ float Ws[];  // [K*CIN][cout]
   const int K = p.K, cout = p.cout;
   for (int e = threadIdx.x; e < K * CIN * cout; e += blockDim.x) Ws[e] = __ldg(p.W + e);
@@ -225,20 +228,46 @@ __global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvPar
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int half = (ksize & 1) ? ksize / 2 : 0;
+  const int reach = (ksize - 1) * step;
+  const int lim = kAxisBias - reach;
+  // offsets of the first four rounds (all of a 5x5x5 kernel) are per-lane constants: deltas, packed-key addend, and --
+  // for the inner 3x3x3 offsets -- the column of the stride-1 3x3x3 neighbour table this probe also fills (nbr3)
+  constexpr int RR = 4;
+  LaneOffset fr[RR];
+  int k3r[RR];
+#pragma unroll
+  for (int r = 0; r < RR; ++r) {
+    const int k = r * 32 + lane;
+    fr[r] = lane_offset(k < K ? k : 0, ksize, half, step);
+    const int ax = fr[r].dx / step, ay = fr[r].dy / step, az = fr[r].dz / step;
+    const bool inner = k < K && ax >= -1 && ax <= 1 && ay >= -1 && ay <= 1 && az >= -1 && az <= 1;
+    k3r[r] = inner ? (ax + 1) + 3 * (ay + 1) + 9 * (az + 1) : -1;
+  }
   for (int64_t o = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); o < p.n_out; o += (int64_t)gridDim.x * wpb) {
     const int4 c = __ldg(reinterpret_cast<const int4*>(coords4) + o);
+    const bool safe = (unsigned)c.x < 1023u && c.y >= -lim && c.y < lim && c.z >= -lim && c.z < lim && c.w >= -lim && c.w < lim;
+    const uint64_t base = safe ? pack_key(c.x, c.y, c.z, c.w) : 0ull;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};          // output channels lane, lane+32, lane+64, lane+96
-    for (int k0 = 0; k0 < K; k0 += 32) {
+    unsigned key3 = 0, mask3 = 0;
+    auto round = [&](int k0, const LaneOffset& f, int k3) {
       const int k = k0 + lane;
       int idx = -1;
       if (k < K) {
-        int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
-        int x = c.y + (ix - half) * step, y = c.z + (iy - half) * step, z = c.w + (iz - half) * step;
-        if (coord_in_range(c.x, x, y, z)) idx = hash_find(t, pack_key(c.x, x, y, z));
+        if (safe) idx = hash_find(t, base + (uint64_t)f.dkey);
+        else {
+          const int x = c.y + f.dx, y = c.z + f.dy, z = c.w + f.dz;
+          if (coord_in_range(c.x, x, y, z)) idx = hash_find(t, pack_key(c.x, x, y, z));
+        }
       }
-      float f[CIN];
+      if (nbr3) {    // uniform branch
+        if (k3 >= 0) nbr3[o * 27 + k3] = idx;
+        const bool hit = k3 >= 0 && idx >= 0;
+        key3 |= __reduce_or_sync(0xffffffffu, hit ? (unsigned)f.dirbits : 0u);
+        mask3 |= __reduce_or_sync(0xffffffffu, hit ? (1u << k3) : 0u);
+      }
+      float fv[CIN];
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) f[ci] = idx >= 0 ? __ldg(p.in0 + (size_t)idx * CIN + ci) : 0.f;
+      for (int ci = 0; ci < CIN; ++ci) fv[ci] = idx >= 0 ? __ldg(p.in0 + (size_t)idx * CIN + ci) : 0.f;
       unsigned m = __ballot_sync(0xffffffffu, idx >= 0);
       while (m) {
         const int src = __ffs(m) - 1;
@@ -246,14 +275,29 @@ __global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvPar
         const int kk = k0 + src;
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          const float fv = __shfl_sync(0xffffffffu, f[ci], src);
+          const float v = __shfl_sync(0xffffffffu, fv[ci], src);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int n = lane + 32 * q;
-            if (n < cout) acc[q] = fmaf(fv, Ws[(kk * CIN + ci) * cout + n], acc[q]);
+            if (n < cout) acc[q] = fmaf(v, Ws[(kk * CIN + ci) * cout + n], acc[q]);
           }
         }
       }
+    };
+#pragma unroll
+    for (int r = 0; r < RR; ++r)
+      if (r * 32 < K) round(r * 32, fr[r], k3r[r]);
+    for (int k0 = RR * 32; k0 < K; k0 += 32) {      // kernels wider than 5x5x5: offsets recomputed per round
+      const int k = k0 + lane;
+      const LaneOffset f = lane_offset(k < K ? k : 0, ksize, half, step);
+      const int ax = f.dx / step, ay = f.dy / step, az = f.dz / step;
+      const bool inner = k < K && ax >= -1 && ax <= 1 && ay >= -1 && ay <= 1 && az >= -1 && az <= 1;
+      round(k0, f, inner ? (ax + 1) + 3 * (ay + 1) + 9 * (az + 1) : -1);
+    }
+    if (nbr3 && lane == 0) {
+      if (row_keys) row_keys[o] = (uint8_t)key3;
+      if (row_masks) row_masks[o] = mask3;
+      if (key_hist) atomicAdd(&key_hist[(int64_t)key3 * hist_blocks + (o >> 10)], 1);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -439,12 +483,15 @@ int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, 
 int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
                           int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
                           const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
-                          void* stream) {
+                          int32_t* nbr3_out, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist, void* stream) {
   GCLB_CHECK_ARG(W && table && (n == 0 || (in && coords4 && out)), "null pointer");
   GCLB_CHECK_ARG(cin >= 1 && cin <= 4 && cout >= 1 && cout <= 128, "fused-probe convolution covers cin <= 4, cout <= 128");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && tensor_stride >= 1 && dilation >= 1, "bad kernel geometry");
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0, "bad capacity");
   GCLB_CHECK_ARG(relu == 0 || relu == 1, "relu must be 0 or 1");
+  GCLB_CHECK_ARG(!nbr3_out || ((ksize & 1) && ksize >= 3), "the 3x3x3 table can be emitted by an odd kernel >= 3 only");
+  GCLB_CHECK_ARG(nbr3_out || (!row_keys && !row_masks && !key_hist), "row keys / masks / histogram describe nbr3_out");
+  GCLB_CHECK_ARG(!key_hist || row_keys, "key_hist needs row_keys");
   if (n == 0) return GCLB_OK;
   const int K = ksize * ksize * ksize;
   const size_t smem = (size_t)K * cin * cout * 4;
@@ -456,7 +503,8 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (n + 7) / 8;
     if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(p, t, coords4, ksize, tensor_stride * dilation);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(p, t, coords4, ksize, tensor_stride * dilation, nbr3_out, row_keys, row_masks,
+                                              key_hist, (n + 1023) / 1024);
   };
   if (cin == 1) launch(spconv_fwd_probe_small_cin_kernel<1>);
   else if (cin == 2) launch(spconv_fwd_probe_small_cin_kernel<2>);

@@ -169,10 +169,12 @@ class ResUNetEngine:
       return ops.kernel_map(in_cm, out_cm, ks, transposed=transposed)
 
     recipes = {}
+    # the fused-probe conv1 (odd kernel >= 3) writes the stride-1 3x3x3 table itself, inside forward()
+    fused_k3s1 = self.conv1_probe and self.conv1_ks >= 3 and self.conv1_ks % 2 == 1
     if self.conv1_ks != 1 and not self.conv1_probe:
       recipes["c1"] = lambda: table(cm1, cm1, self.conv1_ks, tc=(self.conv1_ks == 3))
     for s in (1, 2, 4, 8):
-      if not (s == 1 and self.conv1_ks == 3 and "c1" in recipes):
+      if not (s == 1 and ((self.conv1_ks == 3 and "c1" in recipes) or fused_k3s1)):
         recipes[f"k3s{s}"] = (lambda s=s: table(cms[s], cms[s], 3))
     for s in (1, 2, 4):
       recipes[f"down{s}"] = (lambda s=s: table(cms[s], cms[2 * s], 3))
@@ -216,7 +218,12 @@ class ResUNetEngine:
     x = feats.contiguous().float()
     if self.conv1_probe:
       W, sc, sh = self.p["conv1"]
-      c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
+      if "k3s1" in km:
+        c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
+      else:   # conv1's inner probes are the stride-1 3x3x3 kernel map: emitted by the same kernel, bucketed here
+        c1, (t, keys) = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, emit_k3=True)
+        sort = bool(self.tc) and self.sort_rows
+        km.put("k3s1", ((t,) + ops.kernel_map_sort(t, keys, copy=True)) if sort else t, None)
     else:
       c1 = self._conv("conv1", x, km["c1"] if self.conv1_ks != 1 else None, n1, out_dtype=self._want("block1.1"))
     # every layer writes the storage dtype its consumer reads (fp16 between the 64..256-channel layers, fp32 at the

@@ -241,16 +241,28 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
 
 
 def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int, dilation: int = 1, scale=None,
-                     shift=None, residual=None, relu=False) -> torch.Tensor:
+                     shift=None, residual=None, relu=False, emit_k3: bool = False):
   """stride-1 convolution of a narrow input (cin <= 4) with the kernel map fused into the kernel (hash probes instead
-  of a neighbour table): conv1 of the ResUNet."""
+  of a neighbour table): conv1 of the ResUNet.  emit_k3: also return the stride-1 3x3x3 kernel map of `cm` that the
+  inner probes amount to, as (nbr [n, 27], (row_keys, row_masks, key_hist)) -- the same objects kernel_map(cm, cm, 3,
+  with_keys=True) builds with a separate pass."""
   require_cuda(x, W)
   K, cin, cout = W.shape
   assert K == ksize ** 3 and x.shape[1] == cin and x.shape[0] == cm.n
-  out = torch.empty((cm.n, cout), dtype=torch.float32, device=x.device)
+  dev = x.device
+  out = torch.empty((cm.n, cout), dtype=torch.float32, device=dev)
+  nbr = keys = masks = hist = None
+  if emit_k3:
+    assert ksize % 2 == 1 and ksize >= 3 and dilation == 1
+    nbr = torch.empty((cm.n, 27), dtype=torch.int32, device=dev)
+    keys = torch.empty(cm.n, dtype=torch.uint8, device=dev)
+    masks = torch.empty(cm.n, dtype=torch.int32, device=dev)
+    hist = torch.zeros((64, (cm.n + 1023) // 1024), dtype=torch.int32, device=dev)
   call("gclb_spconv_fwd_probe", ptr(x.contiguous()), cin, ptr(W.contiguous()), ksize, cout, ptr(cm.table), cm.capacity,
        ptr(cm.coords), cm.n, cm.tensor_stride, dilation, ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
-       ptr(out), stream())
+       ptr(out), ptr(nbr), ptr(keys), ptr(masks), ptr(hist), stream())
+  if emit_k3:
+    return out, (nbr, (keys, masks, hist))
   return out
 
 

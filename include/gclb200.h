@@ -170,11 +170,15 @@ int gclb_spconv_fwd(const void* in0, int32_t c0, const void* in1, int32_t c1, in
                     int64_t n_out, int32_t algo, void* stream);
 /* stride-1 convolution with a small input width (cin <= 4, e.g. conv1 of ResUNet: cin = 1, kernel 5^3) with the kernel
  * map FUSED into the convolution: the kernel probes the coordinate hash of the (single) coordinate map itself, so no
- * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd. */
+ * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd.
+ * nbr3_out int32 [n, 27] or NULL (odd ksize >= 3): the probes of the inner 3x3x3 offsets ARE the stride-1 3x3x3 kernel
+ * map of the same coordinate map (what the next layers, block1 of the ResUNet, convolve over), so the kernel can write
+ * that table -- with row_keys / row_masks / key_hist exactly as gclb_kmap_build produces them (all optional, key_hist
+ * caller-zeroed) -- and the separate gclb_kmap_build pass for it disappears. */
 int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
                           int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
                           const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
-                          void* stream);
+                          int32_t* nbr3_out, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist, void* stream);
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
                       const int32_t* nbr, int32_t K, float* gW, void* stream);

@@ -365,6 +365,24 @@ def test_spconv_two_source_and_pointwise(G):
   assert _rel(got_mm, a @ W1[:64]) < FP32_TOL
 
 
+@pytest.mark.parametrize("ks", [3, 5, 7])
+def test_probe_conv_emits_k3_table(G, ks):
+  """the inner probes of the fused-probe convolution ARE the stride-1 3x3x3 kernel map: table, row keys, row masks and
+  key histogram must equal what the separate gclb_kmap_build pass produces, bit for bit (and the conv output is unchanged)"""
+  torch.manual_seed(33)
+  C_ref, _ = _oracle_voxelize([_random_cloud(29, 4000, 9.0), _random_cloud(30, 1500, 5.0)], 0.3)
+  cm = G.ops.hash_build(C_ref.to(G.dev))
+  x = torch.randn(cm.n, 1, device=G.dev)
+  W = torch.randn(ks ** 3, 1, 32, device=G.dev)
+  ref_out = G.ops.spconv_fwd_probe(x, W, cm, ks)
+  out, (nbr, (keys, masks, hist)) = G.ops.spconv_fwd_probe(x, W, cm, ks, emit_k3=True)
+  assert torch.equal(out, ref_out)
+  nbr_ref, (k_ref, m_ref, h_ref) = G.ops.kernel_map(cm, cm, 3, with_keys=True)
+  assert torch.equal(nbr, nbr_ref) and torch.equal(keys, k_ref) and torch.equal(masks, m_ref) and torch.equal(hist, h_ref)
+  onbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(3, 1))
+  assert np.array_equal(nbr.cpu().numpy(), onbr)
+
+
 @pytest.mark.parametrize("cin,cout,ks", [(1, 32, 5), (3, 16, 3), (4, 64, 3)])
 def test_spconv_probe_fused_kernel_map(G, cin, cout, ks):
   torch.manual_seed(31)
