@@ -20,8 +20,8 @@ SIGNATURES = {
     "gclb_has_tcgen05": (C.c_int, []),
     "gclb_hash_capacity": (_i64, [_i64]),
     "gclb_hash_bytes": (_sz, [_i64]),
-    "gclb_hash_build": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
-    "gclb_hash_query": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
+    "gclb_hash_build": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p]),
+    "gclb_hash_query": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p]),
     "gclb_compact_workspace_bytes": (_sz, [_i64]),
     "gclb_voxelize": (C.c_int, [_p, _i64, _p, _i32, _f32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_quantize_rows": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),

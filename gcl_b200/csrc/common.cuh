@@ -66,49 +66,95 @@ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 fmix64
   return (uint32_t)k;
 }
 
-// One 16-byte slot = { uint64 key, uint32 value (row index), uint32 pad }: a probe is ONE 128-bit load (key and value
-// arrive together: no dependent second load on a hit), and the whole table is initialised by a single memset(0xFF)
-// (empty key = ~0, value = UINT_MAX so that atomicMin(row) works on it).
-struct __align__(16) HashSlot {
+// One 32-byte slot (= one memory sector) holds a QUAD: four cells that are consecutive along x at the table's tensor stride
+//   { uint64 group key, uint32 val[0..1] | uint32 val[2..3], 8 bytes unused }        val = row index, ~0 = no such cell
+// group key = the packed cell key with its x field replaced by (x_field >> shift) >> 2, sub-cell = (x_field >> shift) & 3,
+// shift = log2(tensor stride).  A kernel-map probe of the 3 (5) x-neighbours of a voxel therefore touches 1-2 sectors
+// instead of 3 (5) -- the kernel-map and fused-probe kernels are bound by L2 sector traffic, see DESIGN.md -- while
+// single-cell insert / find keep their semantics (first-occurrence winner via atomicMin on val[sub]).
+// The whole table is initialised by a single memset(0xFF) (empty key = ~0, empty val = UINT_MAX = -1 as a row index).
+struct __align__(32) HashSlot {
   unsigned long long key;
-  unsigned int val;
-  unsigned int pad;
+  unsigned int val[4];
+  unsigned long long pad;
 };
 struct HashTable {
   HashSlot* slots;
-  uint32_t mask;  // capacity - 1
+  uint32_t mask;  // number of quad slots - 1
+  int shift;      // log2(tensor stride of the coordinates stored)
 };
 constexpr unsigned int kValEmpty = 0xffffffffu;
-__host__ __device__ __forceinline__ HashTable make_table(const void* buf, int64_t capacity) {
+constexpr uint64_t kXFieldMask = 0x3FFFFull << 36;
+__host__ __device__ __forceinline__ int log2_pow2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+__host__ __device__ __forceinline__ HashTable make_table(const void* buf, int64_t capacity, int tensor_stride) {
   HashTable t;
   t.slots = (HashSlot*)buf;
   t.mask = (uint32_t)(capacity - 1);
+  t.shift = tensor_stride > 1 ? log2_pow2(tensor_stride) : 0;
   return t;
 }
-__device__ __forceinline__ int table_val(const HashTable& t, int slot) { return (int)t.slots[slot].val; }
+// cell key -> (group key, sub-cell)
+__device__ __forceinline__ uint64_t group_of(const HashTable& t, uint64_t key, int& sub) {
+  const uint32_t cell = (uint32_t)((key >> 36) & 0x3FFFFu) >> t.shift;
+  sub = (int)(cell & 3u);
+  return (key & ~kXFieldMask) | ((uint64_t)(cell >> 2) << 36);
+}
+// handle = quad * 4 + sub: what insert returns and the compaction passes store per input row
+__device__ __forceinline__ unsigned int& table_val_ref(const HashTable& t, int handle) {
+  return t.slots[handle >> 2].val[handle & 3];
+}
+__device__ __forceinline__ int table_val(const HashTable& t, int handle) { return (int)table_val_ref(t, handle); }
 
-// insert key, value = min(existing, row).  Returns slot, or -1 when the table is full.  *old_val (optional) receives the
-// previous value (kValEmpty when the slot was fresh).
+// insert key, value = min(existing, row).  Returns the handle, or -1 when the table is full.  *old_val (optional) receives
+// the previous value (kValEmpty when the cell was fresh).
 __device__ __forceinline__ int hash_insert_min(const HashTable& t, uint64_t key, int row, unsigned int* old_val = nullptr) {
-  uint32_t slot = hash_key(key) & t.mask;
+  int sub;
+  const uint64_t g = group_of(t, key, sub);
+  uint32_t slot = hash_key(g) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; ++probe) {
     unsigned long long prev = t.slots[slot].key;
-    if (prev == kEmptyKey) prev = atomicCAS(&t.slots[slot].key, kEmptyKey, (unsigned long long)key);
-    if (prev == kEmptyKey || prev == key) {
-      unsigned int o = atomicMin(&t.slots[slot].val, (unsigned int)row);
+    if (prev == kEmptyKey) prev = atomicCAS(&t.slots[slot].key, kEmptyKey, (unsigned long long)g);
+    if (prev == kEmptyKey || prev == g) {
+      unsigned int o = atomicMin(&t.slots[slot].val[sub], (unsigned int)row);
       if (old_val) *old_val = o;
-      return (int)slot;
+      return (int)(slot * 4u + (uint32_t)sub);
     }
     slot = (slot + 1) & t.mask;
   }
   return -1;
 }
-__device__ __forceinline__ int hash_find(const HashTable& t, uint64_t key) {
-  uint32_t slot = hash_key(key) & t.mask;
+// the four row indices of a quad (all -1 when the group is absent): ONE sector, two 128-bit loads
+__device__ __forceinline__ void quad_find(const HashTable& t, uint64_t gkey, int (&v)[4]) {
+  uint32_t slot = hash_key(gkey) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; ++probe) {
-    const uint4 s = __ldg(reinterpret_cast<const uint4*>(t.slots + slot));   // one 128-bit load: key + value
-    const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
-    if (k == key) return (int)s.z;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(t.slots + slot));   // key + val[0..1]
+    const unsigned long long k = ((unsigned long long)a.y << 32) | a.x;
+    if (k == gkey) {
+      const uint2 b = __ldg(reinterpret_cast<const uint2*>(t.slots + slot) + 2);   // val[2..3], same sector
+      v[0] = (int)a.z; v[1] = (int)a.w; v[2] = (int)b.x; v[3] = (int)b.y;
+      return;
+    }
+    if (k == kEmptyKey) break;
+    slot = (slot + 1) & t.mask;
+  }
+  v[0] = v[1] = v[2] = v[3] = -1;
+}
+__device__ __forceinline__ int hash_find(const HashTable& t, uint64_t key) {
+  int sub;
+  const uint64_t g = group_of(t, key, sub);
+  uint32_t slot = hash_key(g) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(t.slots + slot));
+    const unsigned long long k = ((unsigned long long)a.y << 32) | a.x;
+    if (k == g) {
+      if (sub == 0) return (int)a.z;
+      if (sub == 1) return (int)a.w;
+      return (int)__ldg(&t.slots[slot].val[sub]);
+    }
     if (k == kEmptyKey) return -1;
     slot = (slot + 1) & t.mask;
   }

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kCompactBlock) scatter_winners_kernel(Src src,
     if (unique_map_out) unique_map_out[pos] = i;
     // the table now maps coordinate -> compacted row.  Safe against concurrent is_winner() of duplicates:
     // pos <= i < (any losing row index), so a loser can never read its own index here.
-    t.slots[slot_of[i]].val = (unsigned int)pos;
+    table_val_ref(t, slot_of[i]) = (unsigned int)pos;
   }
 }
 
@@ -157,14 +157,15 @@ __global__ void __launch_bounds__(256) inverse_map_kernel(int64_t n, const int64
 }
 
 template <class Src>
-static int dedupe_rows(Src src, int64_t n, const int64_t* n_dev, void* table, int64_t capacity, int32_t* coords4_out,
+static int dedupe_rows(Src src, int64_t n, const int64_t* n_dev, void* table, int64_t capacity, int tensor_stride,
+                       int32_t* coords4_out,
                        int64_t* unique_map_out, int32_t* inverse_out, int64_t* n_out, int32_t* status,
                        void* workspace, cudaStream_t st) {
   if (capacity < 2 || (capacity & (capacity - 1)) != 0 || capacity < n) {
     set_error("hash capacity must be a power of two >= the number of rows");
     return GCLB_ERR_ARG;
   }
-  HashTable t = make_table(table, capacity);
+  HashTable t = make_table(table, capacity, tensor_stride);
   cudaMemsetAsync(t.slots, 0xff, (size_t)capacity * sizeof(HashSlot), st);
   if (n == 0) {
     cudaMemsetAsync(n_out, 0, 8, st);
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(256) hash_build_kernel(const int32_t* c4, int6
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int4 c = __ldg(reinterpret_cast<const int4*>(c4) + i);
-  if (!coord_in_range(c.x, c.y, c.z, c.w)) { atomicOr(status, GCLB_ST_RANGE); return; }
+  const int am = (1 << t.shift) - 1;     // rows of a map at tensor stride s sit on multiples of s
+  if (!coord_in_range(c.x, c.y, c.z, c.w) || ((c.y | c.z | c.w) & am)) { atomicOr(status, GCLB_ST_RANGE); return; }
   unsigned int old = kValEmpty;
   int slot = hash_insert_min(t, pack_key(c.x, c.y, c.z, c.w), (int)i, &old);
   if (slot < 0) atomicOr(status, GCLB_ST_FULL);
@@ -214,11 +216,12 @@ int gclb_version(void) { return 100; }
 int64_t gclb_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int64_t gclb_hash_capacity(int64_t n_rows) {
-  // load factor <= 0.25: 73 % of kernel-map probes are misses, and an unsuccessful linear-probe search costs
-  // (1 + 1/(1-a)^2)/2 slots (2.5 at a = 0.5, 1.4 at 0.25); measured: sparser tables beat smaller, denser ones even
-  // when the denser table fits L2 better
+  // capacity counts 32-byte QUAD slots (4 x-consecutive cells each).  2 quads per row: <= 0.5 load even if every row
+  // sat in its own quad, ~0.25-0.3 on LiDAR maps (1.8-2 rows share a quad).  Most kernel-map probes are misses, and an
+  // unsuccessful linear-probe search costs (1 + 1/(1-a)^2)/2 slots (2.5 at a = 0.5, 1.4 at 0.25); measured: sparser
+  // tables beat smaller, denser ones even when the denser table fits L2 better
   int64_t c = 1024;
-  while (c < 4 * n_rows) c <<= 1;
+  while (c < 2 * n_rows) c <<= 1;
   return c;
 }
 size_t gclb_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot); }
@@ -227,25 +230,28 @@ size_t gclb_compact_workspace_bytes(int64_t n) {
   return (size_t)(((n + 3) & ~3ll) + compact_blocks(n) + 8) * 4;
 }
 
-int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64_t n, int32_t* status, void* stream) {
+int gclb_hash_build(void* table, int64_t capacity, int32_t tensor_stride, const int32_t* coords4, int64_t n, int32_t* status,
+                    void* stream) {
   GCLB_CHECK_ARG(table && status && (n == 0 || coords4), "null pointer");
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity >= n, "bad capacity");
+  GCLB_CHECK_ARG(tensor_stride >= 1 && (tensor_stride & (tensor_stride - 1)) == 0, "tensor stride must be a power of two");
   cudaStream_t st = (cudaStream_t)stream;
-  HashTable t = make_table(table, capacity);
+  HashTable t = make_table(table, capacity, tensor_stride);
   cudaMemsetAsync(t.slots, 0xff, (size_t)capacity * sizeof(HashSlot), st);
   if (n > 0) { hash_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(coords4, n, t, status); count_launches(1); }
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
 
-int gclb_hash_query(const void* table, int64_t capacity, const int32_t* q4, int64_t nq, int32_t* rows_out,
-                    void* stream) {
+int gclb_hash_query(const void* table, int64_t capacity, int32_t tensor_stride, const int32_t* q4, int64_t nq,
+                    int32_t* rows_out, void* stream) {
   GCLB_CHECK_ARG(table && (nq == 0 || (q4 && rows_out)), "null pointer");
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0, "bad capacity");
+  GCLB_CHECK_ARG(tensor_stride >= 1 && (tensor_stride & (tensor_stride - 1)) == 0, "tensor stride must be a power of two");
   if (nq > 0) count_launches(1);
   if (nq > 0)
-    hash_query_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_table(table, capacity), q4,
-                                                                                     nq, rows_out);
+    hash_query_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_table(table, capacity, tensor_stride),
+                                                                                     q4, nq, rows_out);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }
@@ -258,7 +264,7 @@ int gclb_voxelize(const float* xyz, int64_t P, const int64_t* cloud_ptr, int32_t
   GCLB_CHECK_ARG(voxel > 0.f && n_clouds >= 1 && n_clouds < 1023, "bad voxel size or cloud count");
   GCLB_CHECK_ARG(P < (1ll << 31), "too many points for int32 row indices");
   XyzSource src{xyz, cloud_ptr, n_clouds, voxel};
-  return dedupe_rows(src, P, nullptr, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status,
+  return dedupe_rows(src, P, nullptr, table, capacity, 1, coords4_out, unique_map_out, inverse_map_out, n_out, status,
                      workspace, (cudaStream_t)stream);
 }
 
@@ -270,8 +276,8 @@ int gclb_quantize_rows(const int32_t* rows, int64_t P, int32_t width, void* tabl
   GCLB_CHECK_ARG(width == 3 || width == 4, "width must be 3 or 4");
   GCLB_CHECK_ARG(P < (1ll << 31), "too many rows for int32 row indices");
   RowsSource src{rows, width};
-  return dedupe_rows(src, P, nullptr, table, capacity, coords4_out, unique_map_out, inverse_map_out, n_out, status, workspace,
-                     (cudaStream_t)stream);
+  return dedupe_rows(src, P, nullptr, table, capacity, 1, coords4_out, unique_map_out, inverse_map_out, n_out, status,
+                     workspace, (cudaStream_t)stream);
 }
 
 int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in_dev, int32_t new_stride,
@@ -279,10 +285,10 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
                     int32_t* status, void* workspace, void* stream) {
   GCLB_CHECK_ARG(out_table && n_out && status && workspace, "null pointer");
   GCLB_CHECK_ARG(n_in == 0 || (in_coords4 && out_coords4), "null pointer");
-  GCLB_CHECK_ARG(new_stride >= 1, "stride must be >= 1");
+  GCLB_CHECK_ARG(new_stride >= 1 && (new_stride & (new_stride - 1)) == 0, "tensor stride must be a power of two");
   StrideSource src{in_coords4, new_stride};
-  return dedupe_rows(src, n_in, n_in_dev, out_table, out_capacity, out_coords4, nullptr, parent_row_out, n_out, status,
-                     workspace, (cudaStream_t)stream);
+  return dedupe_rows(src, n_in, n_in_dev, out_table, out_capacity, new_stride, out_coords4, nullptr, parent_row_out, n_out,
+                     status, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

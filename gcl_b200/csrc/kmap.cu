@@ -18,9 +18,15 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
   const int warps_per_block = blockDim.x >> 5;
   const int half = (ksize & 1) ? ksize / 2 : 0;
   const int reach = (ksize - 1) * step;                 // |delta| never exceeds this on any axis
-  const int amask = in_stride > 1 ? in_stride - 1 : 0;  // tensor strides are powers of two
+  const int amask = (1 << t.shift) - 1;                 // tensor strides are powers of two
   // the first 32 offsets (all of a 3x3x3 map) never change: keep their deltas in registers, no div/mod per row
   const LaneOffset f0 = lane_offset(lane < K ? lane : 0, ksize, half, sign * step);
+  // 3x3x3 map whose offsets step by exactly one cell of the probed table (self maps and coarse-from-fine maps): the three
+  // x-neighbours of a column (dy, dz) live in at most two quads, so 18 lanes (2 quads x 9 columns) fetch the whole
+  // neighbourhood with 18 one-sector probes instead of 27
+  const bool quad_path = (ksize == 3) && (step == (1 << t.shift));
+  const int qg = lane / 9, qcol = lane % 9;               // quad 0/1 of the column, column = (dy, dz)
+  const int qdy = qcol % 3 - 1, qdz = qcol / 3 - 1;       // actual coordinate deltas in units of `step`
   const int64_t o0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int64_t ostep = (int64_t)gridDim.x * warps_per_block;
   int4 c_next = o0 < n_out ? __ldg(reinterpret_cast<const int4*>(out_c4) + o0) : make_int4(0, 0, 0, 0);
@@ -33,25 +39,56 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
     const uint64_t base = safe ? pack_key(c.x, c.y, c.z, c.w) : 0ull;
     int key = 0;
     unsigned rmask = 0;
-    for (int k0 = 0; k0 < K; k0 += 32) {
-      const int k = k0 + lane;
-      const LaneOffset f = (k0 == 0) ? f0 : lane_offset(k < K ? k : 0, ksize, half, sign * step);
-      int r = -1;
-      if (k < K) {
-        const int x = c.y + f.dx, y = c.z + f.dy, z = c.w + f.dz;
-        // rows of the probed map sit on multiples of ITS tensor stride: a misaligned candidate (19 of the 27 offsets of
-        // every fine voxel of a transposed map) cannot exist and is rejected without touching the table
-        const bool aligned = ((x | y | z) & amask) == 0;
-        if (aligned) {
-          if (safe) r = hash_find(t, base + (uint64_t)f.dkey);
-          else if (coord_in_range(c.x, x, y, z)) r = hash_find(t, pack_key(c.x, x, y, z));
+    if (quad_path && safe) {
+      const int cx = (c.y + kAxisBias) >> t.shift;          // biased cell index along x
+      const int g0 = (cx - 1) >> 2;
+      unsigned bits = 0, dirs = 0;
+      if (lane < 18 && (qg == 0 || ((cx + 1) >> 2) != g0)) {
+        const int gx = g0 + qg;
+        const uint64_t gkey = ((uint64_t)(unsigned)c.x << 54) | ((uint64_t)(unsigned)gx << 36) |
+                              ((uint64_t)(unsigned)(c.z + qdy * step + kAxisBias) << 18) |
+                              (uint64_t)(unsigned)(c.w + qdz * step + kAxisBias);
+        int v[4];
+        quad_find(t, gkey, v);
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+          const int cell = cx + j;
+          if ((cell >> 2) != gx) continue;
+          const int r = v[cell & 3];
+          // table column of the actual delta (j, qdy, qdz): offsets are sign * (i - 1)
+          const int ix = sign * j + 1, iy = sign * qdy + 1, iz = sign * qdz + 1;
+          const int k = ix + 3 * iy + 9 * iz;
+          nbr[o * 27 + k] = r;
+          if (r >= 0) {
+            bits |= 1u << k;
+            dirs |= (ix < 1 ? 1 : 0) | (ix > 1 ? 2 : 0) | (iy < 1 ? 4 : 0) | (iy > 1 ? 8 : 0) | (iz < 1 ? 16 : 0) | (iz > 1 ? 32 : 0);
+            if (pair_count) atomicAdd(&s_count[k], 1);
+          }
         }
-        nbr[o * K + k] = r;
-        if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
       }
-      if (row_masks && k0 == 0) rmask = __ballot_sync(0xffffffffu, r >= 0);   // populated offsets of this row (K <= 32)
-      // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
-      if (row_keys) key |= (int)__reduce_or_sync(0xffffffffu, (unsigned)(r >= 0 ? f.dirbits : 0));
+      if (row_masks) rmask = __reduce_or_sync(0xffffffffu, bits);
+      if (row_keys) key = (int)__reduce_or_sync(0xffffffffu, dirs);
+    } else {
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        const LaneOffset f = (k0 == 0) ? f0 : lane_offset(k < K ? k : 0, ksize, half, sign * step);
+        int r = -1;
+        if (k < K) {
+          const int x = c.y + f.dx, y = c.z + f.dy, z = c.w + f.dz;
+          // rows of the probed map sit on multiples of ITS tensor stride: a misaligned candidate (19 of the 27 offsets
+          // of every fine voxel of a transposed map) cannot exist and is rejected without touching the table
+          const bool aligned = ((x | y | z) & amask) == 0;
+          if (aligned) {
+            if (safe) r = hash_find(t, base + (uint64_t)f.dkey);
+            else if (coord_in_range(c.x, x, y, z)) r = hash_find(t, pack_key(c.x, x, y, z));
+          }
+          nbr[o * K + k] = r;
+          if (r >= 0 && pair_count) atomicAdd(&s_count[k], 1);
+        }
+        if (row_masks && k0 == 0) rmask = __ballot_sync(0xffffffffu, r >= 0);   // populated offsets of this row (K <= 32)
+        // 6-bit neighbour-direction key of the row (see gclb_kmap_sort_rows), for free while the row is in registers
+        if (row_keys) key |= (int)__reduce_or_sync(0xffffffffu, (unsigned)(r >= 0 ? f.dirbits : 0));
+      }
     }
     if (row_keys && lane == 0) {
       row_keys[o] = (uint8_t)key;
@@ -235,14 +272,14 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
   GCLB_CHECK_ARG(row_masks == nullptr || ksize * ksize * ksize <= 32, "row masks need ksize^3 <= 32");
   GCLB_CHECK_ARG(key_hist == nullptr || row_keys != nullptr, "key_hist needs row_keys");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && offset_stride >= 1 && dilation >= 1 && (sign == 1 || sign == -1) &&
-                     in_tensor_stride >= 0 && (in_tensor_stride & (in_tensor_stride - 1)) == 0,
+                     in_tensor_stride >= 1 && (in_tensor_stride & (in_tensor_stride - 1)) == 0,
                  "bad kernel geometry");
   if (n_out == 0) return GCLB_OK;
   int K = ksize * ksize * ksize;
   int64_t blocks = (n_out + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
-      make_table(in_table, in_capacity), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, in_tensor_stride,
+      make_table(in_table, in_capacity, in_tensor_stride), out_coords4, n_out, ksize, K, offset_stride * dilation, sign, in_tensor_stride,
       nbr, pair_count, row_keys, row_masks, key_hist, compact_blocks(n_out));
   count_launches(1);
   GCLB_CHECK_LAUNCH();

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) spconv_fwd_small_cin_kernel(ConvParams p)
 // itself (32 offsets at a time).  For conv1 (K = 125) this removes the 4*K*n-byte table write + read (163 MB per 325k
 // voxels) and its separate build pass; the probes hit the L2-resident hash table.
 template <int CIN>
-__global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvParams p, HashTable t,
+__global__ void __launch_bounds__(256, 4) spconv_fwd_probe_small_cin_kernel(ConvParams p, HashTable t,
                                                                           const int32_t* __restrict__ coords4, int ksize,
                                                                           int step, int32_t* __restrict__ nbr3,
                                                                           uint8_t* __restrict__ row_keys,
@@ -230,25 +230,93 @@ __global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvPar
   const int half = (ksize & 1) ? ksize / 2 : 0;
   const int reach = (ksize - 1) * step;
   const int lim = kAxisBias - reach;
-  // offsets of the first four rounds (all of a 5x5x5 kernel) are per-lane constants: deltas, packed-key addend, and --
-  // for the inner 3x3x3 offsets -- the column of the stride-1 3x3x3 neighbour table this probe also fills (nbr3)
-  constexpr int RR = 4;
-  LaneOffset fr[RR];
-  int k3r[RR];
+  const bool quad5 = (ksize == 5) && (step == (1 << t.shift));
+  // quad path: lane l probes item l (round 0) and item 32 + l (round 1, lanes 0-17) of the 2 quads x 25 columns
+  int q_g[2], q_dy[2], q_dz[2];
 #pragma unroll
-  for (int r = 0; r < RR; ++r) {
-    const int k = r * 32 + lane;
-    fr[r] = lane_offset(k < K ? k : 0, ksize, half, step);
-    const int ax = fr[r].dx / step, ay = fr[r].dy / step, az = fr[r].dz / step;
-    const bool inner = k < K && ax >= -1 && ax <= 1 && ay >= -1 && ay <= 1 && az >= -1 && az <= 1;
-    k3r[r] = inner ? (ax + 1) + 3 * (ay + 1) + 9 * (az + 1) : -1;
+  for (int r = 0; r < 2; ++r) {
+    const int item = (r * 32 + lane) % 50, col = item % 25;
+    q_g[r] = item / 25;
+    q_dy[r] = col % 5 - 2;
+    q_dz[r] = col / 5 - 2;
   }
-  for (int64_t o = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); o < p.n_out; o += (int64_t)gridDim.x * wpb) {
-    const int4 c = __ldg(reinterpret_cast<const int4*>(coords4) + o);
+  const int64_t o_first = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5), o_step = (int64_t)gridDim.x * wpb;
+  int4 c_next = o_first < p.n_out ? __ldg(reinterpret_cast<const int4*>(coords4) + o_first) : make_int4(0, 0, 0, 0);
+  for (int64_t o = o_first; o < p.n_out; o += o_step) {
+    const int4 c = c_next;                        // the next row's coordinates are already in flight
+    if (o + o_step < p.n_out) c_next = __ldg(reinterpret_cast<const int4*>(coords4) + o + o_step);
     const bool safe = (unsigned)c.x < 1023u && c.y >= -lim && c.y < lim && c.z >= -lim && c.z < lim && c.w >= -lim && c.w < lim;
     const uint64_t base = safe ? pack_key(c.x, c.y, c.z, c.w) : 0ull;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};          // output channels lane, lane+32, lane+64, lane+96
     unsigned key3 = 0, mask3 = 0;
+    if (quad5 && safe) {
+      // 5x5x5 kernel stepping by one cell of the table: the five x-neighbours of a column (dy, dz) live in exactly two
+      // quads => 50 one-sector probes (2 quads x 25 columns, two rounds of lanes) instead of 125.  The row is
+      // latency-bound (table probe -> feature load), so both rounds' probes are issued together, then all eight feature
+      // loads, and only then the FMA loops.
+      const int cx = (c.y + kAxisBias) >> t.shift;
+      const int g0 = (cx - 2) >> 2;
+      unsigned kbits = 0, mbits = 0;
+      int v[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int gx = g0 + q_g[r];
+        const uint64_t gkey = ((uint64_t)(unsigned)c.x << 54) | ((uint64_t)(unsigned)gx << 36) |
+                              ((uint64_t)(unsigned)(c.z + q_dy[r] * step + kAxisBias) << 18) |
+                              (uint64_t)(unsigned)(c.w + q_dz[r] * step + kAxisBias);
+        if (r == 0 || lane < 18) quad_find(t, gkey, v[r]);
+        else v[r][0] = v[r][1] = v[r][2] = v[r][3] = -1;
+      }
+      int idx[2][4], kk_[2][4];
+      float fv[2][4][CIN];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int gx = g0 + q_g[r];
+        const int dy = q_dy[r], dz = q_dz[r];
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const int j = (gx << 2) + sub - cx;                    // x delta of this cell, in cells
+          const bool inwin = (r == 0 || lane < 18) && j >= -2 && j <= 2;
+          idx[r][sub] = inwin ? v[r][sub] : -1;
+          kk_[r][sub] = (j + 2) + 5 * (dy + 2) + 25 * (dz + 2);
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) fv[r][sub][ci] = idx[r][sub] >= 0 ? __ldg(p.in0 + (size_t)idx[r][sub] * CIN + ci) : 0.f;
+          if (nbr3 && inwin && j >= -1 && j <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1) {
+            const int k3 = (j + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+            nbr3[o * 27 + k3] = idx[r][sub];
+            if (idx[r][sub] >= 0) {
+              mbits |= 1u << k3;
+              kbits |= (j < 0 ? 1 : 0) | (j > 0 ? 2 : 0) | (dy < 0 ? 4 : 0) | (dy > 0 ? 8 : 0) | (dz < 0 ? 16 : 0) | (dz > 0 ? 32 : 0);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          unsigned m = __ballot_sync(0xffffffffu, idx[r][sub] >= 0);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int kk = __shfl_sync(0xffffffffu, kk_[r][sub], src);
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+              const float xv = __shfl_sync(0xffffffffu, fv[r][sub][ci], src);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int n = lane + 32 * q;
+                if (n < cout) acc[q] = fmaf(xv, Ws[(kk * CIN + ci) * cout + n], acc[q]);
+              }
+            }
+          }
+        }
+      }
+      if (nbr3) {
+        key3 = __reduce_or_sync(0xffffffffu, kbits);
+        mask3 = __reduce_or_sync(0xffffffffu, mbits);
+      }
+    } else {
     auto round = [&](int k0, const LaneOffset& f, int k3) {
       const int k = k0 + lane;
       int idx = -1;
@@ -284,15 +352,13 @@ __global__ void __launch_bounds__(256) spconv_fwd_probe_small_cin_kernel(ConvPar
         }
       }
     };
-#pragma unroll
-    for (int r = 0; r < RR; ++r)
-      if (r * 32 < K) round(r * 32, fr[r], k3r[r]);
-    for (int k0 = RR * 32; k0 < K; k0 += 32) {      // kernels wider than 5x5x5: offsets recomputed per round
+    for (int k0 = 0; k0 < K; k0 += 32) {      // generic kernels: offsets recomputed per round (not the hot path)
       const int k = k0 + lane;
       const LaneOffset f = lane_offset(k < K ? k : 0, ksize, half, step);
       const int ax = f.dx / step, ay = f.dy / step, az = f.dz / step;
       const bool inner = k < K && ax >= -1 && ax <= 1 && ay >= -1 && ay <= 1 && az >= -1 && az <= 1;
       round(k0, f, inner ? (ax + 1) + 3 * (ay + 1) + 9 * (az + 1) : -1);
+    }
     }
     if (nbr3 && lane == 0) {
       if (row_keys) row_keys[o] = (uint8_t)key3;
@@ -497,7 +563,8 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
   const size_t smem = (size_t)K * cin * cout * 4;
   GCLB_CHECK_ARG(smem <= 200 * 1024, "weights do not fit in shared memory");
   ConvParams p{in, nullptr, cin, 0, W, K, cout, nullptr, nullptr, nullptr, scale, shift, residual, relu, out, n};
-  HashTable t = make_table(table, capacity);
+  GCLB_CHECK_ARG(tensor_stride >= 1 && (tensor_stride & (tensor_stride - 1)) == 0, "tensor stride must be a power of two");
+  HashTable t = make_table(table, capacity, tensor_stride);
   cudaStream_t st = (cudaStream_t)stream;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

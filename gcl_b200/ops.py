@@ -23,7 +23,9 @@ def _new_table(n_rows: int, device, upper_bound: bool = False) -> Tuple[torch.Te
   """upper_bound: n_rows is a host-side bound (point count / parent rows) far above the rows that will be inserted, so
   half the usual slack already gives a very low load factor (and halves the memset)."""
   lib = _lib.load()
-  cap = int(lib.gclb_hash_capacity(int(n_rows + 1) // 2 if upper_bound else int(n_rows)))
+  # 2 quad slots per row when the row count is exact; 1.34 per row (load <= 0.75 even if every row were its own quad, ~0.1
+  # in practice) when n_rows is a bound
+  cap = int(lib.gclb_hash_capacity((2 * int(n_rows) + 2) // 3 if upper_bound else int(n_rows)))
   return torch.empty(int(lib.gclb_hash_bytes(cap)), dtype=torch.uint8, device=device), cap
 
 
@@ -39,7 +41,7 @@ def hash_build(coords4: torch.Tensor, tensor_stride: int = 1, check: bool = True
   n = coords4.shape[0]
   table, cap = _new_table(n, coords4.device)
   status = torch.zeros(1, dtype=torch.int32, device=coords4.device)
-  call("gclb_hash_build", ptr(table), cap, ptr(coords4), n, ptr(status), stream())
+  call("gclb_hash_build", ptr(table), cap, int(tensor_stride), ptr(coords4), n, ptr(status), stream())
   if check:
     _lib.check_status(status, "SparseTensor coordinates")
   return CoordMap(coords4, table, cap, n, tensor_stride)
@@ -49,7 +51,7 @@ def hash_query(cm: CoordMap, q4: torch.Tensor) -> torch.Tensor:
   require_cuda(q4)
   q4 = q4.to(torch.int32).contiguous()
   out = torch.empty(q4.shape[0], dtype=torch.int32, device=q4.device)
-  call("gclb_hash_query", ptr(cm.table), cm.capacity, ptr(q4), q4.shape[0], ptr(out), stream())
+  call("gclb_hash_query", ptr(cm.table), cm.capacity, int(cm.tensor_stride), ptr(q4), q4.shape[0], ptr(out), stream())
   return out
 
 

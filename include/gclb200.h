@@ -45,18 +45,22 @@ int gclb_has_tcgen05(void);
 
 /* ------------------------------------------------------------------------------------------------------
  * Coordinate hash table: open addressing, linear probing, 64-bit packed keys, 32-bit values (row index).
- * Layout in the caller's buffer: capacity 16-byte slots { uint64 key; uint32 value; uint32 pad } (16-byte aligned), so
- * a probe is one 128-bit load.
+ * Layout in the caller's buffer: `capacity` 32-byte QUAD slots { uint64 group key; uint32 value[4]; 8 bytes unused }
+ * (32-byte aligned = one memory sector).  A quad holds the four cells (b, x, y, z) with the same (b, floor(x/4s), y, z),
+ * s = the map's tensor stride (a power of two; rows sit on multiples of s): the x-neighbours a kernel-map probe wants
+ * arrive with one sector instead of one sector each.  Every entry point that takes a table also takes the tensor
+ * stride it was built with.
  * Replaces ME's CoordinateMapGPU insert/find (SparseTensor construction: scripts/test_kitti.py:143-148,
  * lib/colocation_trainer.py:843-845, util/misc.py:128).
  * ---------------------------------------------------------------------------------------------------- */
-int64_t gclb_hash_capacity(int64_t n_rows);           /* power of two >= 4*n_rows, >= 1024 */
+int64_t gclb_hash_capacity(int64_t n_rows);           /* quad slots: power of two >= 2*n_rows, >= 1024 */
 size_t gclb_hash_bytes(int64_t capacity);
 /* insert N unique rows; vals = row index.  Duplicates keep the smallest row index and set GCLB_ST_DUPLICATE. */
-int gclb_hash_build(void* table, int64_t capacity, const int32_t* coords4, int64_t n, int32_t* status, void* stream);
+int gclb_hash_build(void* table, int64_t capacity, int32_t tensor_stride, const int32_t* coords4, int64_t n,
+                    int32_t* status, void* stream);
 /* rows_out[q] = row index of q4[q] or -1 */
-int gclb_hash_query(const void* table, int64_t capacity, const int32_t* q4, int64_t nq, int32_t* rows_out,
-                    void* stream);
+int gclb_hash_query(const void* table, int64_t capacity, int32_t tensor_stride, const int32_t* q4, int64_t nq,
+                    int32_t* rows_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K1 voxelisation = ME.utils.sparse_quantize(xyz / voxel, return_index=True) + floor().int() + sparse_collate
@@ -101,8 +105,10 @@ int gclb_stride_map(const int32_t* in_coords4, int64_t n_in, const int64_t* n_in
  * Forward conv (model/resunet.py:38-95, residual_block.py:23-33): in_table = input map, out_coords = output
  * map, offset_stride = input tensor stride, sign=+1.  Transposed conv (model/resunet.py:101-134): in_table =
  * coarse map, out_coords = fine map, offset_stride = fine tensor stride, sign=-1.
- *   in_tensor_stride: tensor stride of the probed (input) map, or 0/1 if unknown: candidates not aligned to it are
- *            rejected without a table access (most offsets of a transposed map).
+ *   in_tensor_stride: tensor stride the probed (input) table was built with (power of two, >= 1; REQUIRED: it fixes
+ *            the quad layout): candidates not aligned to it are rejected without a table access (most offsets of a
+ *            transposed map); 3x3x3 maps whose offsets step by exactly this stride fetch a whole column's x-neighbours
+ *            with 1-2 quad probes (18 sectors per row instead of 27).
  *   pair_count int32 [K] or NULL: number of valid entries per offset (caller-zeroed).
  *   row_keys uint8 [n_out] or NULL: 6-bit neighbour-direction key of every row, computed for free during the build
  *            and accepted by gclb_kmap_sort_rows.

@@ -38,15 +38,15 @@ def test_ctypes_table_matches_header():
 def test_host_side_helpers(lib):
   assert lib.gclb_version() >= 100
   assert lib.gclb_hash_capacity(0) == 1024
-  assert lib.gclb_hash_capacity(1000) == 4096
-  assert lib.gclb_hash_capacity(130000) == 524288
-  assert lib.gclb_hash_bytes(1024) == 1024 * 16
+  assert lib.gclb_hash_capacity(1000) == 2048            # quad slots: 2 per row
+  assert lib.gclb_hash_capacity(130000) == 262144
+  assert lib.gclb_hash_bytes(1024) == 1024 * 32
   assert lib.gclb_compact_workspace_bytes(5000) >= 5000 * 4
   assert lib.gclb_nn_workspace_bytes(100, 200, 1, 100, 200) >= 300 * 8
 
 
 def test_argument_errors_are_reported_not_crashed(lib):
-  rc = lib.gclb_hash_build(None, 1024, None, 10, None, None)
+  rc = lib.gclb_hash_build(None, 1024, 1, None, 10, None, None)
   assert rc == -1 and b"null" in lib.gclb_last_error()
   rc = lib.gclb_spconv_fwd(None, 0, None, 0, 0, None, 1, 1, None, None, None, None, None, None, 0, None, 0, 0, None)
   assert rc == -1
