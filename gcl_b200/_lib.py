@@ -35,7 +35,7 @@ SIGNATURES = {
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,
                                         _p, _p, _p, _p, _p]),
     "gclb_weights_to_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
-    "gclb_weights_to_tc_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "gclb_weights_to_tc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "gclb_spconv_wgrad": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _i32, _p, _p]),
     "gclb_spconv_wgrad_tc": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _p, _i32, _p, _p]),
     "gclb_pointwise_tail": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p]),

@@ -6,6 +6,8 @@
 // atomics, deterministic) with BatchNorm(eval)/bias, residual add and ReLU fused into the store.
 // This path is exact fp32 and also serves dgrad (conv with the transposed table / transposed weights).
 // The tensor-core path (tcgen05 kind::tf32, accumulators in TMEM) lives in spconv_tc.cu.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace gclb {
@@ -371,7 +373,9 @@ __global__ void __launch_bounds__(256, 4) spconv_fwd_probe_small_cin_kernel(Conv
       if (n < cout) {
         float v = acc[q] * (p.scale ? __ldg(p.scale + n) : 1.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
         if (p.residual) v += __ldg(p.residual + (size_t)o * cout + n);
-        p.out[(size_t)o * cout + n] = (p.relu & 1) ? fmaxf(v, 0.f) : v;
+        v = (p.relu & 1) ? fmaxf(v, 0.f) : v;
+        if (p.relu & 16) reinterpret_cast<__half*>(p.out)[(size_t)o * cout + n] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        else p.out[(size_t)o * cout + n] = v;
       }
     }
   }
@@ -503,10 +507,10 @@ int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, 
   GCLB_CHECK_ARG(nbr || K == 1, "nbr may be NULL only for K == 1");
   GCLB_CHECK_ARG(n_in == 0 || in0, "null input");
   GCLB_CHECK_ARG(algo >= 0 && algo <= 2, "algo must be 0, 1 or 2");
-  GCLB_CHECK_ARG(relu >= 0 && relu <= 31,
+  GCLB_CHECK_ARG(relu >= 0 && relu <= 63,
                  "relu flags: bit 0 = ReLU, bit 1 = L2-normalise rows, bit 2 = nbr is the re-ordered copy, bit 3 = fp16 "
-                 "inputs/residual/weights, bit 4 = fp16 output (bits 1-4: tcgen05 path)");
-  GCLB_CHECK_ARG(algo == 2 || (relu & 30) == 0, "flag bits 1-4 exist on the tcgen05 path only");
+                 "inputs/residual/weights, bit 4 = fp16 output, bit 5 = 32-channel fp16 rows (bits 1-5: tcgen05 path)");
+  GCLB_CHECK_ARG(algo == 2 || (relu & 62) == 0, "flag bits 1-5 exist on the tcgen05 path only");
   GCLB_CHECK_ARG((relu & 4) == 0 || row_perm != nullptr, "flag bit 2 needs row_perm");
   GCLB_CHECK_ARG(row_perm == nullptr || (algo == 2 && nbr != nullptr), "row_perm is a tcgen05-path option and needs nbr");
   GCLB_CHECK_ARG(tile_mask == nullptr || (algo == 2 && nbr != nullptr && K <= 32), "tile_mask is a tcgen05-path option");
@@ -548,13 +552,14 @@ int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, 
 
 int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
                           int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
-                          const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                          const float* scale, const float* shift, const float* residual, int32_t relu, void* out_,
                           int32_t* nbr3_out, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist, void* stream) {
+  float* out = static_cast<float*>(out_);
   GCLB_CHECK_ARG(W && table && (n == 0 || (in && coords4 && out)), "null pointer");
   GCLB_CHECK_ARG(cin >= 1 && cin <= 4 && cout >= 1 && cout <= 128, "fused-probe convolution covers cin <= 4, cout <= 128");
   GCLB_CHECK_ARG(ksize >= 1 && ksize <= 7 && tensor_stride >= 1 && dilation >= 1, "bad kernel geometry");
   GCLB_CHECK_ARG(capacity >= 2 && (capacity & (capacity - 1)) == 0, "bad capacity");
-  GCLB_CHECK_ARG(relu == 0 || relu == 1, "relu must be 0 or 1");
+  GCLB_CHECK_ARG((relu & ~17) == 0, "relu flags: bit 0 = ReLU, bit 4 = fp16 output");
   GCLB_CHECK_ARG(!nbr3_out || ((ksize & 1) && ksize >= 3), "the 3x3x3 table can be emitted by an odd kernel >= 3 only");
   GCLB_CHECK_ARG(nbr3_out || (!row_keys && !row_masks && !key_hist), "row keys / masks / histogram describe nbr3_out");
   GCLB_CHECK_ARG(!key_hist || row_keys, "key_hist needs row_keys");

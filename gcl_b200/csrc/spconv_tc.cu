@@ -21,15 +21,20 @@
 
 namespace gclb {
 
-constexpr int KSLAB = 32;             // channels per stage = one 128-byte swizzle row
-constexpr int A_BYTES = TM * 128;     // 16 KB
+constexpr int KSLAB = 32;             // tf32: channels per stage = one 128-byte swizzle row
+// operand modes: 0 = fp32 activations, kind::tf32, 32 channels per 128-byte row (SWIZZLE_128B)
+//                1 = fp16 activations, kind::f16,  64 channels per 128-byte row (SWIZZLE_128B)
+//                2 = fp16 activations, kind::f16,  32 channels per  64-byte row (SWIZZLE_64B): sources whose width is a
+//                    multiple of 32 but not of 64 (the 32-channel stride-1 level of the ResUNet)
 constexpr int kGatherWarps = 8;
 constexpr int kMmaWarp = 8, kNbrWarp = 9;
 constexpr int kTcThreads = 14 * 32;   // 448: warps 10-13 are the epilogue
 
-template <int COUT>
+template <int COUT, int MODE = 0>
 struct TcCfg {
-  static constexpr int B_BYTES = COUT * 128;
+  static constexpr int ROWB = MODE == 2 ? 64 : 128;       // bytes per operand row
+  static constexpr int A_BYTES = TM * ROWB;               // 16 KB / 8 KB
+  static constexpr int B_BYTES = COUT * ROWB;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   // deepest ring that leaves room for two neighbour tiles (2 x 14 KB) in 227 KB
   static constexpr int STAGES = COUT >= 256 ? 4 : (COUT >= 128 ? 5 : (COUT >= 64 ? 7 : 8));
@@ -48,11 +53,14 @@ struct TcShared {   // static shared: barriers + small per-tile metadata
   int act_k[4][32];
 };
 
-template <int COUT, int KVOL, bool HALF>
+template <int COUT, int KVOL, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
                                                                       const __grid_constant__ CUtensorMap map0,
                                                                       const __grid_constant__ CUtensorMap map1) {
-  using Cfg = TcCfg<COUT>;
+  using Cfg = TcCfg<COUT, MODE>;
+  constexpr bool HALF = MODE != 0;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int ROWB = Cfg::ROWB;
   constexpr int S = Cfg::STAGES;
   constexpr int NBUF = Cfg::NBUF, NACC = Cfg::NACC;
   constexpr int NBR_INTS = TM * KVOL;
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // HALF: activations (in0, in1, residual) are IEEE fp16 in HBM, weights an fp16 image, MMA kind::f16 -- a 128-byte
   // operand row then holds 64 channels instead of 32: half the gather bytes, same 10-bit mantissa as kind::tf32
-  constexpr int KCH = HALF ? 64 : 32;
+  constexpr int KCH = MODE == 1 ? 64 : 32;
   const int cin = p.c0 + p.c1;
   const int slabs = cin / KCH;
   const bool identity = (p.nbr == nullptr);     // K == 1 `mm` path: nbr[o] = o
@@ -125,8 +133,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
                    Cfg::B_BYTES, &sh.full[stage]);
         }
         __syncwarp();                                        // the barrier is armed before any gather can complete on it
-        if (c < p.c0) tma_gather4(a_s + lane * 512, &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
-        else tma_gather4(a_s + lane * 512, &map1, &sh.full[stage], c - p.c0, r[0], r[1], r[2], r[3]);
+        if (c < p.c0) tma_gather4(a_s + lane * (4 * ROWB), &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
+        else tma_gather4(a_s + lane * (4 * ROWB), &map1, &sh.full[stage], c - p.c0, r[0], r[1], r[2], r[3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.nbr_empty[b]);   // this warp no longer reads the neighbour tile
@@ -155,8 +163,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
           const uint32_t b_s = a_s + A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {   // 4 MMAs of 32 bytes of K (8 tf32 / 16 fp16) inside the 128-byte swizzle row
-            if (HALF) umma_f16(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+          for (int ks = 0; ks < ROWB / 32; ++ks) {   // MMAs of 32 bytes of K (8 tf32 / 16 fp16) inside the swizzle row
+            if (MODE == 2) umma_f16(d_tmem, make_desc_sw64(a_s + ks * 32), make_desc_sw64(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+            else if (MODE == 1) umma_f16(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
             else umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
           }
           umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
@@ -355,26 +364,28 @@ __global__ void __launch_bounds__(256) weights_to_tc_kernel(const float* __restr
 
 // fp16 image: per (k, 64-channel slab) one cout x 128 B block (row n = 64 halves, 16-byte chunk j at (j ^ n%8)),
 // values rounded to nearest-even fp16 (saturating).
+// slab == 32: per (k, 32-channel slab) one cout x 64 B block in the SWIZZLE_64B layout (16-byte chunk j at j ^ ((n/2)%4)).
 __global__ void __launch_bounds__(256) weights_to_tc_f16_kernel(const float* __restrict__ W, int K, int cin, int cout,
-                                                                __half* __restrict__ Wimg) {
+                                                                int slab, __half* __restrict__ Wimg) {
   const int64_t total = (int64_t)K * cin * cout;
-  const int slabs = cin / 64;
+  const int slabs = cin / slab;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(e % cout);
     const int c = (int)((e / cout) % cin);
     const int k = (int)(e / ((int64_t)cout * cin));
-    const int sl = c / 64, cc = c % 64, j = cc >> 3, w = cc & 7;
-    const int64_t blk = ((int64_t)k * slabs + sl) * ((int64_t)cout * 64);
-    const int off = (n >> 3) * 512 + (n & 7) * 64 + ((j ^ (n & 7)) << 3) + w;     // in halves
+    const int sl = c / slab, cc = c % slab, j = cc >> 3, w = cc & 7;
+    const int64_t blk = ((int64_t)k * slabs + sl) * ((int64_t)cout * slab);
+    const int off = slab == 64 ? (n >> 3) * 512 + (n & 7) * 64 + ((j ^ (n & 7)) << 3) + w     // in halves
+                               : n * 32 + ((j ^ ((n >> 1) & 3)) << 3) + w;
     Wimg[blk + off] = __float2half_rn(fminf(fmaxf(W[e], -65504.f), 65504.f));
   }
 }
 
-template <int COUT, int KVOL, bool HALF>
+template <int COUT, int KVOL, int MODE>
 static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
-  using Cfg = TcCfg<COUT>;
+  using Cfg = TcCfg<COUT, MODE>;
   size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
-  auto kern = spconv_fwd_tc_kernel<COUT, KVOL, HALF>;
+  auto kern = spconv_fwd_tc_kernel<COUT, KVOL, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -383,8 +394,8 @@ static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   const int num_tiles = (int)((p.n_out + TM - 1) / TM);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;     // persistent: one CTA per SM
   CUtensorMap map0, map1;
-  int rc = make_rows_tensor_map_ex(&map0, p.in0, n_in, p.c0, HALF, false);
-  if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, HALF, false) : (map1 = map0, GCLB_OK);
+  int rc = make_rows_tensor_map_ex(&map0, p.in0, n_in, p.c0, MODE, false);
+  if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, MODE, false) : (map1 = map0, GCLB_OK);
   if (rc != GCLB_OK) return rc;
   kern<<<grid, kTcThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
   e = cudaGetLastError();
@@ -398,7 +409,8 @@ static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
 
 bool spconv_tc_supported(const ConvParams& p) {
   const int cin = p.c0 + p.c1;
-  const int kch = (p.relu & 8) ? 64 : KSLAB;     // fp16 operands: 64 channels per 128-byte row
+  const int kch = ((p.relu & 8) && !(p.relu & 32)) ? 64 : KSLAB;     // fp16 operands: 64 channels per 128-byte row unless bit 5
+  if ((p.relu & 32) && !(p.relu & 8)) return false;
   if (p.c0 % kch != 0 || p.c1 % kch != 0 || cin < kch) return false;
   if ((p.relu & 16) && ((p.relu >> 1) & 1)) return false;   // the fused L2 normalise writes fp32 descriptors
   if (!(p.cout == 32 || p.cout == 64 || p.cout == 128 || p.cout == 256)) return false;
@@ -410,8 +422,9 @@ bool spconv_tc_supported(const ConvParams& p) {
 int spconv_fwd_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
 #define GCLB_TC_CASE(C)                                                                                \
   case C:                                                                                              \
-    if (p.relu & 8) return p.K == 27 ? launch_tc<C, 27, true>(p, n_in, st) : launch_tc<C, 1, true>(p, n_in, st); \
-    return p.K == 27 ? launch_tc<C, 27, false>(p, n_in, st) : launch_tc<C, 1, false>(p, n_in, st);
+    if (p.relu & 32) return p.K == 27 ? launch_tc<C, 27, 2>(p, n_in, st) : launch_tc<C, 1, 2>(p, n_in, st); \
+    if (p.relu & 8) return p.K == 27 ? launch_tc<C, 27, 1>(p, n_in, st) : launch_tc<C, 1, 1>(p, n_in, st);   \
+    return p.K == 27 ? launch_tc<C, 27, 0>(p, n_in, st) : launch_tc<C, 1, 0>(p, n_in, st);
   switch (p.cout) {
     GCLB_TC_CASE(32)
     GCLB_TC_CASE(64)
@@ -442,13 +455,16 @@ int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, flo
   return GCLB_OK;
 }
 
-int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, void* Wt, void* stream) {
+int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, int32_t slab_channels, void* Wt,
+                           void* stream) {
   GCLB_CHECK_ARG(W && Wt && K >= 1 && cin >= 1 && cout >= 1, "bad arguments");
-  GCLB_CHECK_ARG(cin % 64 == 0 && cout % 8 == 0, "fp16 tensor-core image needs cin % 64 == 0 and cout % 8 == 0");
+  GCLB_CHECK_ARG(slab_channels == 64 || slab_channels == 32, "slab_channels must be 64 or 32");
+  GCLB_CHECK_ARG(cin % slab_channels == 0 && cout % 8 == 0, "fp16 tensor-core image needs cin % slab_channels == 0 and cout % 8 == 0");
   int64_t total = (int64_t)K * cin * cout;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  weights_to_tc_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, reinterpret_cast<__half*>(Wt));
+  weights_to_tc_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, slab_channels,
+                                                                                   reinterpret_cast<__half*>(Wt));
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -74,6 +74,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major SWIZZLE_64B (64-byte rows, 16-byte chunks XOR (row / 2) % 4): 8-row groups 512 B apart, layout type 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -129,6 +134,7 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
 int make_rows_tensor_map(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows);
 int make_rows_tensor_map_sw(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows, bool atom32);
 // general form: rows of fp32 (box = 32 channels) or fp16 (box = 64 channels), 128 bytes per box row either way
-int make_rows_tensor_map_ex(CUtensorMap* map, const void* base, int64_t n, int c, bool half, bool atom32);
+// mode 0 fp32 x 32 ch (SWIZZLE_128B), 1 fp16 x 64 ch (SWIZZLE_128B), 2 fp16 x 32 ch (SWIZZLE_64B)
+int make_rows_tensor_map_ex(CUtensorMap* map, const void* base, int64_t n, int c, int mode, bool atom32);
 
 }  // namespace gclb

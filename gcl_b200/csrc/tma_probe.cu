@@ -20,27 +20,29 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_rows_tensor_map_any(CUtensorMap* map, const void* base, int64_t n, int c, int box_rows, bool half, bool atom32);
+int make_rows_tensor_map_any(CUtensorMap* map, const void* base, int64_t n, int c, int box_rows, int mode, bool atom32);
 
 // 2-D fp32 tensor map over a row-major [n, c] matrix, box = box_rows x 32 channels; atom32 selects
 // SWIZZLE_128B_ATOM_32B (32-byte chunks XOR row % 4: the only layout tcgen05 accepts for MN-major tf32 operands)
 // instead of the plain SWIZZLE_128B (16-byte chunks XOR row % 8) the K-major operands use.
 int make_rows_tensor_map_sw(CUtensorMap* map, const float* base, int64_t n, int c, int box_rows, bool atom32) {
-  return make_rows_tensor_map_any(map, base, n, c, box_rows, false, atom32);
+  return make_rows_tensor_map_any(map, base, n, c, box_rows, 0, atom32);
 }
-int make_rows_tensor_map_ex(CUtensorMap* map, const void* base, int64_t n, int c, bool half, bool atom32) {
-  return make_rows_tensor_map_any(map, base, n, c, 1, half, atom32);
+int make_rows_tensor_map_ex(CUtensorMap* map, const void* base, int64_t n, int c, int mode, bool atom32) {
+  return make_rows_tensor_map_any(map, base, n, c, 1, mode, atom32);
 }
 
-int make_rows_tensor_map_any(CUtensorMap* map, const void* base, int64_t n, int c, int box_rows, bool half, bool atom32) {
+int make_rows_tensor_map_any(CUtensorMap* map, const void* base, int64_t n, int c, int box_rows, int mode, bool atom32) {
+  const bool half = mode != 0;
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return GCLB_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)c, (cuuint64_t)n};
   cuuint64_t gstride[1] = {(cuuint64_t)c * (half ? 2 : 4)};
-  cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {mode == 1 ? 64u : 32u, (cuuint32_t)box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mode == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return GCLB_ERR_CUDA; }

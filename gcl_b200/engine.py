@@ -96,14 +96,17 @@ class ResUNetEngine:
         if ops.tc_supported(c0, cin - c0, cout, K):
           self.tc[key] = ops.weights_to_tc(W)
         if self.half and ops.tc_supported(c0, cin - c0, cout, K, half=True):
-          self.tc16[key] = ops.weights_to_tc(W, half=True)
+          self.tc16[key] = ops.weights_to_tc(W, half=True, c0=c0)
       # pointwise tail on the tensor cores: [y1 | s1] W1 -> ReLU -> W2 + bias -> L2 normalise (fused in the epilogue)
       c_s1 = type(model).CHANNELS[1]
       c_y1 = self.W1.shape[0] - c_s1
       self.tail_tc = None
       if (ops.tc_supported(c_y1, c_s1, self.W1.shape[1], 1) and ops.tc_supported(self.W2.shape[0], 0, self.W2.shape[1], 1)
           and self.W2.shape[1] == 32):
-        self.tail_tc = (ops.weights_to_tc(self.W1), ops.weights_to_tc(self.W2))
+        if self.half:
+          self.tail_tc = (ops.weights_to_tc(self.W1, half=True, c0=c_y1), ops.weights_to_tc(self.W2, half=True))
+        else:
+          self.tail_tc = (ops.weights_to_tc(self.W1), ops.weights_to_tc(self.W2))
 
   # first-source channel count of the layers that read a concatenation (ME.cat fused into the gather)
   SPLIT = {}
@@ -218,10 +221,11 @@ class ResUNetEngine:
     x = feats.contiguous().float()
     if self.conv1_probe:
       W, sc, sh = self.p["conv1"]
+      od = self._want("block1.1")
       if "k3s1" in km:
-        c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh)
+        c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, out_dtype=od)
       else:   # conv1's inner probes are the stride-1 3x3x3 kernel map: emitted by the same kernel, bucketed here
-        c1, (t, keys) = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, emit_k3=True)
+        c1, (t, keys) = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, emit_k3=True, out_dtype=od)
         sort = bool(self.tc) and self.sort_rows
         km.put("k3s1", ((t,) + ops.kernel_map_sort(t, keys, copy=True)) if sort else t, None)
     else:
@@ -237,11 +241,14 @@ class ResUNetEngine:
                      w("conv3_tr"))
     y2 = self._block("block3_tr", self._conv("conv3_tr", y4, km["up2"], n2, x2=s4, out_dtype=w("block3_tr.1")), km["k3s2"],
                      w("conv2_tr"))
-    y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2, out_dtype=w("block2_tr.1")), km["k3s1"])
-    s1 = s1 if s1.dtype == torch.float32 else s1.float()     # the pointwise tail reads fp32
+    tail_dt = self.tail_tc[0].dtype if getattr(self, "tail_tc", None) is not None else torch.float32
+    y1 = self._block("block2_tr", self._conv("conv2_tr", y2, km["up1"], n1, x2=s2, out_dtype=w("block2_tr.1")), km["k3s1"],
+                     tail_dt)
+    s1 = s1 if s1.dtype == tail_dt else s1.to(tail_dt)        # no-op on the tuned path
     if getattr(self, "tail_tc", None) is not None:
       h = ops.spconv_fwd(y1, self.tail_tc[0], None, n1, in1=s1, relu=True, algo=2)
-      return ops.spconv_fwd(h, self.tail_tc[1], None, n1, shift=self.bias, normalize=self.normalize, algo=2)
+      return ops.spconv_fwd(h, self.tail_tc[1], None, n1, shift=self.bias, normalize=self.normalize, algo=2,
+                            out_dtype=torch.float32)
     return ops.pointwise_tail(y1, s1, self.W1, self.W2, self.bias, normalize=self.normalize)
 
   @torch.no_grad()

@@ -237,13 +237,14 @@ def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], 
   assert out.dtype in (torch.float32, torch.float16) and (algo == 2 or out.dtype == torch.float32)
   flags = int(bool(relu)) | (2 if normalize else 0) | (4 if (row_perm is not None and nbr_is_sorted) else 0)
   flags |= (8 if half else 0) | (16 if out.dtype == torch.float16 else 0)
+  flags |= 32 if (half and f16_slab(c0, c1) == 32) else 0
   call("gclb_spconv_fwd", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(W.contiguous()), K, cout, ptr(nbr),
        ptr(row_perm), ptr(tile_mask), ptr(scale), ptr(shift), ptr(residual), flags, ptr(out), n_out, algo, stream())
   return out
 
 
 def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int, dilation: int = 1, scale=None,
-                     shift=None, residual=None, relu=False, emit_k3: bool = False):
+                     shift=None, residual=None, relu=False, emit_k3: bool = False, out_dtype=torch.float32):
   """stride-1 convolution of a narrow input (cin <= 4) with the kernel map fused into the kernel (hash probes instead
   of a neighbour table): conv1 of the ResUNet.  emit_k3: also return the stride-1 3x3x3 kernel map of `cm` that the
   inner probes amount to, as (nbr [n, 27], (row_keys, row_masks, key_hist)) -- the same objects kernel_map(cm, cm, 3,
@@ -252,7 +253,7 @@ def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int,
   K, cin, cout = W.shape
   assert K == ksize ** 3 and x.shape[1] == cin and x.shape[0] == cm.n
   dev = x.device
-  out = torch.empty((cm.n, cout), dtype=torch.float32, device=dev)
+  out = torch.empty((cm.n, cout), dtype=out_dtype, device=dev)
   nbr = keys = masks = hist = None
   if emit_k3:
     assert ksize % 2 == 1 and ksize >= 3 and dilation == 1
@@ -261,26 +262,37 @@ def spconv_fwd_probe(x: torch.Tensor, W: torch.Tensor, cm: CoordMap, ksize: int,
     masks = torch.empty(cm.n, dtype=torch.int32, device=dev)
     hist = torch.zeros((64, (cm.n + 1023) // 1024), dtype=torch.int32, device=dev)
   call("gclb_spconv_fwd_probe", ptr(x.contiguous()), cin, ptr(W.contiguous()), ksize, cout, ptr(cm.table), cm.capacity,
-       ptr(cm.coords), cm.n, cm.tensor_stride, dilation, ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
-       ptr(out), ptr(nbr), ptr(keys), ptr(masks), ptr(hist), stream())
+       ptr(cm.coords), cm.n, cm.tensor_stride, dilation, ptr(scale), ptr(shift), ptr(residual),
+       int(bool(relu)) | (16 if out_dtype == torch.float16 else 0), ptr(out), ptr(nbr), ptr(keys), ptr(masks), ptr(hist),
+       stream())
   if emit_k3:
     return out, (nbr, (keys, masks, hist))
   return out
 
 
-def weights_to_tc(W: torch.Tensor, half: bool = False) -> torch.Tensor:
+def f16_slab(c0: int, c1: int = 0) -> int:
+  """channels per gathered fp16 row: 64 (128-byte rows) when every source width is a multiple of 64, else 32 (64-byte rows)"""
+  return 64 if (c0 % 64 == 0 and c1 % 64 == 0) else 32
+
+
+def weights_to_tc(W: torch.Tensor, half: bool = False, c0: Optional[int] = None) -> torch.Tensor:
   """[K, Cin, Cout] (or [Cin, Cout]) -> tensor-core image (shape [K, Cout, Cin], pre-swizzled per 32-channel slab,
-  rounded to tf32; half=True: per 64-channel slab, rounded to fp16); done once per layer."""
+  rounded to tf32; half=True: per 64- or 32-channel slab (see f16_slab; c0 = width of the first source of a two-source
+  layer), rounded to fp16); done once per layer."""
   require_cuda(W)
   W3 = (W if W.dim() == 3 else W.unsqueeze(0)).contiguous().float()
   K, cin, cout = W3.shape
   Wt = torch.empty((K, cout, cin), dtype=torch.float16 if half else torch.float32, device=W.device)
-  call("gclb_weights_to_tc_f16" if half else "gclb_weights_to_tc", ptr(W3), K, cin, cout, ptr(Wt), stream())
+  if half:
+    c0 = cin if c0 is None else c0
+    call("gclb_weights_to_tc_f16", ptr(W3), K, cin, cout, f16_slab(c0, cin - c0), ptr(Wt), stream())
+  else:
+    call("gclb_weights_to_tc", ptr(W3), K, cin, cout, ptr(Wt), stream())
   return Wt
 
 
 def tc_supported(c0: int, c1: int, cout: int, K: int, half: bool = False) -> bool:
-  kch = 64 if half else 32
+  kch = 32
   return (_lib.load().gclb_has_tcgen05() == 1 and c0 % kch == 0 and c1 % kch == 0 and c0 >= kch
           and cout in (32, 64, 128, 256) and K in (1, 27))
 

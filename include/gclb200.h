@@ -160,30 +160,35 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
  *               image from gclb_weights_to_tc_f16; the MMA is kind::f16 (fp32 accumulate; fp16 has the 10-bit mantissa
  *               of tf32 but is rounded to nearest when stored, so it is the MORE accurate of the two -- see
  *               tools/precision_study.py) and a gathered 128-byte row carries 64 channels instead of 32: needs
- *               c0 % 64 == 0, c1 % 64 == 0.  bit 4 (16) = `out` is fp16 (saturating round-to-nearest), independent of
- *               bit 3, so a layer can convert in either direction.  scale/shift are always fp32.
+ *               c0 % 64 == 0, c1 % 64 == 0.  bit 5 (32, with bit 3) = the fp16 rows are gathered 32 channels (64 bytes,
+ *               SWIZZLE_64B) at a time, for sources whose width is a multiple of 32 only (W image with slab_channels 32).
+ *               bit 4 (16) = `out` is fp16 (saturating round-to-nearest), independent of bit 3, so a layer can convert
+ *               in either direction.  scale/shift are always fp32.
  * ---------------------------------------------------------------------------------------------------- */
 /* W [K, cin, cout] (ME layout) -> tensor-core image of the same size: per (k, 32-channel slab) one contiguous
  * cout x 128 B block laid out exactly like the SWIZZLE_128B K-major shared-memory tile, values rounded to nearest tf32
  * (done once per layer; needs cin % 32 == 0, cout % 8 == 0) */
 int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream);
-/* same for the fp16 path: per (k, 64-channel slab) one cout x 128 B block of fp16 (round to nearest); Wt holds
- * K*cin*cout halves; needs cin % 64 == 0, cout % 8 == 0 */
-int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, void* Wt, void* stream);
+/* same for the fp16 path: per (k, slab of slab_channels channels) one contiguous block of cout rows of fp16 (round to
+ * nearest) -- slab_channels = 64: 128-byte rows, SWIZZLE_128B (flag bit 3 alone); slab_channels = 32: 64-byte rows,
+ * SWIZZLE_64B (flag bits 3 + 5).  Wt holds K*cin*cout halves; needs cin % slab_channels == 0, cout % 8 == 0 */
+int gclb_weights_to_tc_f16(const float* W, int32_t K, int32_t cin, int32_t cout, int32_t slab_channels, void* Wt,
+                           void* stream);
 int gclb_spconv_fwd(const void* in0, int32_t c0, const void* in1, int32_t c1, int64_t n_in, const void* W,
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
                     const float* scale, const float* shift, const void* residual, int32_t relu_flags, void* out,
                     int64_t n_out, int32_t algo, void* stream);
 /* stride-1 convolution with a small input width (cin <= 4, e.g. conv1 of ResUNet: cin = 1, kernel 5^3) with the kernel
  * map FUSED into the convolution: the kernel probes the coordinate hash of the (single) coordinate map itself, so no
- * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd.
+ * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd
+ * (relu_flags: bit 0 = ReLU, bit 4 = `out` is fp16).
  * nbr3_out int32 [n, 27] or NULL (odd ksize >= 3): the probes of the inner 3x3x3 offsets ARE the stride-1 3x3x3 kernel
  * map of the same coordinate map (what the next layers, block1 of the ResUNet, convolve over), so the kernel can write
  * that table -- with row_keys / row_masks / key_hist exactly as gclb_kmap_build produces them (all optional, key_hist
  * caller-zeroed) -- and the separate gclb_kmap_build pass for it disappears. */
 int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t ksize, int32_t cout, const void* table,
                           int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
-                          const float* scale, const float* shift, const float* residual, int32_t relu, float* out,
+                          const float* scale, const float* shift, const float* residual, int32_t relu_flags, void* out,
                           int32_t* nbr3_out, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist, void* stream);
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,

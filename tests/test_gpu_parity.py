@@ -303,7 +303,7 @@ def test_tc_two_source_epilogue(G):
   assert _rel(got, ref) < FEAT_TOL
 
 
-@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 64), (256, 256), (64, 32), (128, 128)])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 64), (256, 256), (64, 32), (128, 128), (32, 32), (32, 64), (96, 64), (64, 128)])
 def test_tc_fp16_activations(G, cin, cout):
   """kind::f16 path: fp16 activations / residual / weight image, fp32 accumulation, fp32 or fp16 output.
   (a) small integers are exact in fp16: bit-exact against integer arithmetic (pins the 64-channel row layout, the fp16
@@ -315,12 +315,13 @@ def test_tc_fp16_activations(G, cin, cout):
   nbr = OME.build_neighbor_table(C_ref.numpy(), C_ref.numpy(), OME.kernel_offsets(3, 1))
   nbr_d = torch.from_numpy(nbr).int().to(G.dev)
   srt, perm, mask = G.ops.kernel_map_sort(nbr_d)
-  c0 = cin // 2 if cin >= 128 else cin                          # two-source gather for the wide cases
+  # two-source gather for the wide cases; (96: 64 + 32) and (64 -> 128: 32 + 32) take the 32-channel-row layout like (32, *)
+  c0 = cin // 2 if (cin >= 128 or cout == 128) else (64 if cin == 96 else cin)
   xi = torch.randint(-2, 3, (n, cin)).float()
   Wi = torch.randint(-2, 3, (27, cin, cout)).float()
   ri = torch.randint(-2, 3, (n, cout)).float()
   ref = torch.relu(OME.sparse_conv_reference(xi, Wi, nbr, n) + ri)
-  Wh = G.ops.weights_to_tc(Wi.to(G.dev), half=True)
+  Wh = G.ops.weights_to_tc(Wi.to(G.dev), half=True, c0=c0)
   a = xi[:, :c0].contiguous().half().to(G.dev)
   b = xi[:, c0:].contiguous().half().to(G.dev) if c0 < cin else None
   for out_dtype in (torch.float32, torch.float16):
