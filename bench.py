@@ -206,8 +206,15 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
   tot_ms, tot_b, tot_f = sum(ms), sum(r[2] for r in recs), sum(r[3] for r in recs)
   peak = peaks.get("hbm_gbs", 6650.0)
   ach = tot_b / (tot_ms * 1e-3) / 1e9
+  traffic, traffic_src = None, None
+  try:   # DRAM bytes per launch of the same kernels from the committed ncu capture of this build (never measured here)
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v24_conv_traffic.json")))
+    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+  except Exception:
+    pass
   return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-          "traffic": None, "kernel": "spconv_fwd_tc_kernel (tcgen05 sparse conv, all 22 launches of a step incl. the 2 pointwise tail layers)", "launches": len(recs),
+          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(tot_b / max(len(recs), 1)),
+          "kernel": "spconv_fwd_tc_kernel (tcgen05 sparse conv, all 22 launches of a step incl. the 2 pointwise tail layers)", "launches": len(recs),
           "avg_launch_ms": round(tot_ms / len(recs), 4), "conv_ms_per_step": round(tot_ms, 3),
           "algorithmic_bytes_per_step": tot_b, "algorithmic_gflop_per_step": round(tot_f / 1e9, 2),
           "achieved_tflops": round(tot_f / (tot_ms * 1e-3) / 1e12, 2),

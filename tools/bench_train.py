@@ -106,8 +106,15 @@ def main():
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  for _ in range(args.steps):
+  prof = os.environ.get("GCLB_PROFILE_LAST_STEP") == "1"      # tools/profile_step.py --train: ncu range = the last step
+  for i in range(args.steps):
+    if prof and i == args.steps - 1:
+      torch.cuda.synchronize()
+      torch.cuda.profiler.start()
     l = step()
+  if prof:
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
   e1.record()
   torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / args.steps
