@@ -70,48 +70,55 @@ def make_batches(n_batches, pairs_per_batch, seed, n_base=3):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-       "clocks_event_reasons.sw_power_cap")
+  """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML (initialised up front, one
+  light query every 10 ms).  An `nvidia-smi -lms` child process was used first: its start-up (NVML init + device
+  enumeration, hundreds of ms under driver locks) landed inside the ~150 ms timed region and randomly stalled kernel
+  launches (runs of 2400-2500 pairs/s next to 3400 on the same box); NVML in-process does not."""
+  REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
   def __init__(self, gpu_index):
-    self.idx, self.proc, self.lines = gpu_index, None, []
+    self.h = self.nv = None
+    self.sm, self.bits, self.run = [], 0, False
+    self.period = float(os.environ.get("GCLB_CLOCK_PERIOD", "0.05"))
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      try:   # CUDA_VISIBLE_DEVICES may renumber: go through the UUID
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+      except Exception:
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+      self.nv = pynvml
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+      self.h = None
+
+  def _loop(self):
+    nv = self.nv
+    while self.run:
+      try:
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+      except Exception:
+        pass
+      time.sleep(self.period)
 
   def start(self):
-    try:
-      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                    "200", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                   text=True)
-      self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
-      self.t.start()
-    except Exception:
-      self.proc = None
+    if self.h is None:
+      return
+    self.run = True
+    self.t = threading.Thread(target=self._loop, daemon=True)
+    self.t.start()
 
   def stop(self):
-    if self.proc is None:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    time.sleep(0.25)
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=2)
-    except Exception:
-      self.proc.kill()
-    sm, mx, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for l in self.lines:
-      f = [x.strip() for x in l.split(",")]
-      if len(f) < 9:
-        continue
-      try:
-        sm.append(float(f[1])); mx.append(float(f[2]))
-      except ValueError:
-        continue
-      for n, v in zip(names, f[5:9]):
-        if v.lower().startswith("active"):
-          reasons.add(n)
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons), "samples": len(sm)}
+    if self.h is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+    self.run = False
+    if getattr(self, "t", None) is not None:
+      self.t.join(timeout=1)
+    reasons = [name for bit, name in self.REASONS if self.bits & bit]
+    return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+            "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -324,18 +331,20 @@ def main():
     d2h_bytes[0] = pairs.numel() * 8 + pp.numel() * 8
     return out["n_voxels_total"]
 
+  clocks = ClockSampler(local_rank)      # NVML initialised before anything is timed
   for s in range(args.warmup):
     step_resident(s)
   if args.depth > 1:   # warm the per-stream allocator pools of the pipelined path with every batch shape
-    for src in (resident, pinned):
+    for src in (pinned, resident):     # the source of the first timed region last
       for out in matcher.match_many((src[i % n_batches] for i in range(2 * n_batches * args.depth)), depth=args.depth):
         pass
-  clocks = ClockSampler(local_rank)
-  if rank == 0:
+  if rank == 0 and not os.environ.get("GCLB_NO_CLOCKS"):
     clocks.start()
   l0 = lib.gclb_kernel_launches()
+  seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
   ms, nvox = timed_region(step_resident, args.steps, resident)
   launches = lib.gclb_kernel_launches() - l0
+  new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0   # cudaMalloc calls inside the timed region
   clk = clocks.stop() if rank == 0 else None
   for s in range(2):
     step_e2e(s)
@@ -354,15 +363,15 @@ def main():
   line = {"metric": "scan_pairs_per_sec", "value": round(value, 2), "unit": "pairs/s", "n_gpus": world,
           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-          "dtype": "f16/tf32 operands, f32 accumulate" if (lib.gclb_has_tcgen05() and args.algo != 1) else "f32", "data": "synthetic",
+          "dtype": "f16 operands, f32 accumulate" if (lib.gclb_has_tcgen05() and args.algo != 1) else "f32", "data": "synthetic",
           "mvoxels_per_sec": round(nvox / (ms * 1e-3) / 1e6, 3),
           "config": {"workload": workload, "pairs_per_step_per_gpu": args.pairs, "batches_in_flight": args.depth, "parallelism": f"pair-sharded x{world}, no collective",
                      "l2": f"inputs larger than L2: {n_batches} rotating batches, ~{step_ws_mb:.0f} MB algorithmic conv traffic per step vs 126 MB L2",
-                     "conv_algo": ("tcgen05: kind::f16 with fp16 activations for the 64..256-channel layers, kind::tf32 for the 32-channel stride-1 layers and the tail"
+                     "conv_algo": ("tcgen05 kind::f16, fp16 activations between all layers (fp32 accumulate, fp32 BN scale/shift, fp32 descriptors); conv1 (Cin=1) fused hash-probe kernel"
                                    if (lib.gclb_has_tcgen05() and args.algo != 1) else "fp32 CUDA-core implicit GEMM")},
           "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(ms_e2e / args.steps, 3)},
-          "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+          "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": int(new_segments), "clocks": clk, "roofline": roof}
   if world == 1 and not args.no_cpu_baseline:
     r = run_cpu(steps=5, warmup=1, n_pairs_per_step=1)
     line["cpu_baseline"] = {"value": round(r["pairs_per_s"], 4), "unit": "pairs/s", "cores": r["cores"], "kind": "port",

@@ -102,6 +102,64 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(HashTable t, const int3
       if (s_count[k]) atomicAdd(&pair_count[k], s_count[k]);
 }
 
+// Transposed 3x3x3 maps (out = fine map, probed table = the coarse map at twice the offset step): per axis a fine voxel
+// has ONE aligned candidate when its coordinate is even on the coarse lattice (offset 0) and TWO when it is odd (offsets
+// +-1), so a row has at most 8 candidates out of 27.  8 lanes per row (one per candidate), 4 rows per warp; the table is
+// pre-filled with -1 by a memset and only hits are written.  ~4x fewer warp iterations than the lane-per-offset kernel.
+__global__ void __launch_bounds__(256) kmap_build_up_kernel(HashTable t, const int32_t* __restrict__ out_c4, int64_t n_out,
+                                                            int step, int32_t* __restrict__ nbr,
+                                                            int32_t* __restrict__ pair_count, uint8_t* __restrict__ row_keys,
+                                                            uint32_t* __restrict__ row_masks, int32_t* __restrict__ key_hist,
+                                                            int64_t hist_blocks) {
+  __shared__ int s_count[27];
+  if (threadIdx.x < 27) s_count[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xffu << (8 * grp);
+  const int sh = log2_pow2(step);
+  const int64_t rows_per_block = (blockDim.x >> 5) * 4;
+  for (int64_t o = (int64_t)blockIdx.x * rows_per_block + (threadIdx.x >> 5) * 4 + grp; o < n_out;
+       o += (int64_t)gridDim.x * rows_per_block) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(out_c4) + o);
+    const int coord[3] = {c.y, c.z, c.w};
+    int cand[3], idx[3];
+    bool active = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int odd = (coord[a] >> sh) & 1;            // parity on the coarse lattice (two's complement: floor semantics)
+      const int bit = (sub >> a) & 1;
+      if (!odd) {                                       // even: the voxel sits on a coarse cell, offset 0 only
+        active = active && bit == 0;
+        idx[a] = 1;
+        cand[a] = coord[a];
+      } else {                                          // odd: coarse neighbours at +-step (neighbour = c - (i - 1) * step)
+        idx[a] = bit ? 2 : 0;
+        cand[a] = coord[a] + (bit ? -step : step);
+      }
+    }
+    int r = -1;
+    const int k = idx[0] + 3 * idx[1] + 9 * idx[2];
+    if (active && coord_in_range(c.x, cand[0], cand[1], cand[2])) r = hash_find(t, pack_key(c.x, cand[0], cand[1], cand[2]));
+    if (r >= 0) {
+      nbr[o * 27 + k] = r;
+      if (pair_count) atomicAdd(&s_count[k], 1);
+    }
+    const unsigned dirs = r >= 0 ? (unsigned)((idx[0] < 1 ? 1 : 0) | (idx[0] > 1 ? 2 : 0) | (idx[1] < 1 ? 4 : 0) | (idx[1] > 1 ? 8 : 0) |
+                                              (idx[2] < 1 ? 16 : 0) | (idx[2] > 1 ? 32 : 0)) : 0u;
+    const unsigned key = __reduce_or_sync(gmask, dirs);
+    const unsigned rmask = __reduce_or_sync(gmask, r >= 0 ? (1u << k) : 0u);
+    if (sub == 0) {
+      if (row_keys) {
+        row_keys[o] = (uint8_t)key;
+        if (key_hist) atomicAdd(&key_hist[(int64_t)key * hist_blocks + (o >> 10)], 1);
+      }
+      if (row_masks) row_masks[o] = rmask;
+    }
+  }
+  __syncthreads();
+  if (pair_count && threadIdx.x < 27 && s_count[threadIdx.x]) atomicAdd(&pair_count[threadIdx.x], s_count[threadIdx.x]);
+}
+
 // pair lists: flat ordered compaction over e = k*n_out + o
 __global__ void __launch_bounds__(kCompactBlock) kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int K,
                                                                    int32_t* counts) {
@@ -276,6 +334,20 @@ int gclb_kmap_build(const void* in_table, int64_t in_capacity, const int32_t* ou
                  "bad kernel geometry");
   if (n_out == 0) return GCLB_OK;
   int K = ksize * ksize * ksize;
+  const int step = offset_stride * dilation;
+  if (ksize == 3 && sign == -1 && in_tensor_stride == 2 * step && (step & (step - 1)) == 0) {
+    // transposed map onto the next finer level: <= 8 candidates per row (see kmap_build_up_kernel)
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(nbr, 0xff, (size_t)n_out * 27 * sizeof(int32_t), st);
+    int64_t blocks = (n_out + 31) / 32;
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    kmap_build_up_kernel<<<(unsigned)blocks, 256, 0, st>>>(make_table(in_table, in_capacity, in_tensor_stride), out_coords4,
+                                                           n_out, step, nbr, pair_count, row_keys, row_masks, key_hist,
+                                                           compact_blocks(n_out));
+    count_launches(1);
+    GCLB_CHECK_LAUNCH();
+    return GCLB_OK;
+  }
   int64_t blocks = (n_out + 7) / 8;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs/SM
   kmap_build_kernel<<<(unsigned)blocks, 256, K * sizeof(int), (cudaStream_t)stream>>>(
