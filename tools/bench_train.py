@@ -99,8 +99,17 @@ def main():
     opt.step()
     return loss
 
-  for _ in range(3):
-    l0 = step()
+  l0 = step()
+  # warm up until PyTorch's caching allocator stops growing: a cudaMalloc inside the timed steps is a device-wide
+  # synchronisation of unpredictable length (measured: 16 vs 27 ms per step on the same box)
+  seg = lambda: torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+  quiet = 0
+  for _ in range(12):
+    s0 = seg()
+    step()
+    quiet = quiet + 1 if seg() == s0 else 0
+    if quiet >= 3:
+      break
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
