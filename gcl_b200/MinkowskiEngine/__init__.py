@@ -217,7 +217,7 @@ _CONV_ALGO = {"inference": "auto", "training": "fp32"}
 
 def set_training_conv_algo(name: str):
   """'fp32' (default: exact-fp32 forward / dgrad / wgrad, gradients match the reference's arithmetic to ~1e-5) or 'tf32'
-  (forward and dgrad on the tcgen05 kind::tf32 kernel where the layer shape allows, ~1e-3; wgrad stays fp32)."""
+  (forward, dgrad and wgrad on the tcgen05 kind::tf32 kernels where the layer shape allows, ~1e-3)."""
   if name not in ("fp32", "tf32"):
     raise ValueError("algo must be 'fp32' or 'tf32'")
   _CONV_ALGO["training"] = name

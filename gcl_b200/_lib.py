@@ -34,6 +34,9 @@ SIGNATURES = {
                                   _i32, _p]),
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,
                                         _p, _p, _p, _p, _p]),
+    "gclb_groups_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gclb_colocation_groups": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i32, C.c_float, C.c_double, _i32, _i32,
+                                         _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_weights_to_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "gclb_weights_to_tc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "gclb_spconv_wgrad": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _i32, _p, _p]),

@@ -1,6 +1,7 @@
-// K2: kernel maps in output-stationary form.  One warp per output row, lanes over kernel offsets, so the
-// coordinate row is read once (broadcast), the 27 / 125 probes of a row go out together, and the
-// nbr[o*K + k] writes are coalesced.  The hash table of a scan (<= a few MB) lives in L2.
+// K2: kernel maps in output-stationary form.  One warp per output row (4 rows per warp for transposed maps), so the
+// coordinate row is read once (broadcast) and all probes of a row go out together.  Three probing schemes, chosen by the
+// map geometry: quad probes (3x3x3 stepping by one table cell: 18 one-sector probes answer 27 offsets), aligned-candidate
+// probes (transposed maps: <= 8 candidates per row) and the generic lane-per-offset scheme.
 #include "common.cuh"
 
 namespace gclb {

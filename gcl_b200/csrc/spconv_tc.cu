@@ -1,7 +1,9 @@
 // K3 tensor-core path: sparse convolution as an output-stationary implicit GEMM on tcgen05 (sm_100a).
 //
-//   D[128 out rows, Cout] (fp32, TMEM)  +=  A[128 gathered rows, 32 ch] (smem)  x  B[Cout, 32 ch] (smem)
-//   one pipeline stage per (populated kernel offset k, 32-channel slab); 4 x tcgen05.mma.kind::tf32 (K = 8) per stage
+//   D[128 out rows, Cout] (fp32, TMEM)  +=  A[128 gathered rows, one slab] (smem)  x  B[Cout, one slab] (smem)
+//   one pipeline stage per (populated kernel offset k, channel slab); a slab is one 128-byte line of a row: 64 fp16 channels
+//   (kind::f16, K = 16) or 32 fp32 channels (kind::tf32, K = 8) -- 4 tcgen05.mma per stage -- or a 64-byte line of 32 fp16
+//   channels (2 per stage) for tensors whose width is a multiple of 32 only; see the operand modes below
 //
 // Persistent, warp-specialised CTA (one per SM), 448 threads:
 //   warps 0-7   A producers, one WARP per ring slot (stage it belongs to warp it % STAGES): the 128 neighbour rows x 128 B

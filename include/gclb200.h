@@ -276,6 +276,31 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
 int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_rows, int32_t col, const int32_t* rows4_host,
                            float* out256, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Positive-group construction of the GCL colocation loaders:
+ * util/pointcloud.py:69-132 get_matching_indices_colocation, called lib/colocation_data_loader.py:394,672.
+ * Every cloud is the loader's voxel-downsampled cloud (one point per voxel of size `voxel`, in its own sensor frame), so
+ * its voxel hash from gclb_voxelize (table row == point index; the caller checks that no voxel holds two points) stands in
+ * for the reference's Open3D KD-tree.
+ *   center_xyz float32 [n_center, 3] + center_table/center_capacity           (gclb_voxelize of the centre cloud)
+ *   nb_xyz float32 [sum N_j, 3], nb_ptr int64 [J+1] (device), nb_table/nb_capacity (ONE gclb_voxelize call over all
+ *   neighbour clouds, cloud index = batch index)
+ *   trans, inv_trans float64 [J, 4, 4] row-major (device): cloud j -> centre frame and its inverse
+ *   radius: search_voxel_size; K: neighbours kept per cloud, nearest first (K <= 0: every hit, at most kcap <= 32 --
+ *   GCLB_ST_FULL if more exist)
+ * Outputs (device): group_out int64 [<= n_center] sizes of the kept groups in centre-point order, index_out int64
+ * [<= n_center * (1+J) * kcap] concatenated member indices (centre points first, then cloud j offset by
+ * n_center + N_0 + .. + N_{j-1}), finest_out uint8 one-hot per group (util/pointcloud.py:106-116), n_groups_out /
+ * n_index_out int64 [1].  A hit is a point with squared distance < radius^2 in float64 (nanoflann's rule); ties in distance
+ * resolve to the smaller index (implementation-defined in Open3D).
+ * ---------------------------------------------------------------------------------------------------- */
+size_t gclb_groups_workspace_bytes(int64_t n_center, int32_t n_clouds, int32_t kcap);
+int gclb_colocation_groups(const float* center_xyz, int64_t n_center, const void* center_table, int64_t center_capacity,
+                           const float* nb_xyz, const int64_t* nb_ptr, const void* nb_table, int64_t nb_capacity,
+                           const double* trans, const double* inv_trans, int32_t n_clouds, float voxel, double radius,
+                           int32_t K, int32_t kcap, int64_t* group_out, int64_t* index_out, uint8_t* finest_out,
+                           int64_t* n_groups_out, int64_t* n_index_out, int32_t* status, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
 """GPU parity tests: libgclb200 (through the C ABI / the public Python surface) against the CPU oracle on the
 same seeded inputs.  Bit-exact for integer work (voxel indices, hash lookups, kernel maps, NN indices away from
 ties); features within 1e-3 relative (north_star tolerance; fp32 path is held to 1e-5)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -717,3 +719,67 @@ def test_group_loss_fwd_bwd_vs_oracle(G, square, finest):
   assert abs(ng.item() - no.item()) < 1e-5 * max(1, abs(no.item()))
   assert po.item() > 0 and no.item() > 0
   assert _rel(Fg.grad, Fo.grad) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- SURVEY 8f #2
+def _load_group_cases():
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "groups.npz"))
+  for c in range(4):
+    nbs, Ts, j = [], [], 0
+    while f"c{c}_nb{j}" in g:
+      nbs.append(g[f"c{c}_nb{j}"]); Ts.append(g[f"c{c}_T{j}"]); j += 1
+    K = int(g[f"c{c}_K"])
+    yield c, g[f"c{c}_centre"], nbs, Ts, float(g[f"c{c}_radius"]), (None if K < 0 else K), g
+
+
+def test_colocation_groups_vs_reference_fixture(G):
+  """voxel-hash radius search + group assembly on the GPU against the fixture generated by the reference's own
+  get_matching_indices_colocation (util/pointcloud.py:69-132): group sizes, member indices (order included) and the
+  finest-neighbour flags are integer outputs and must match exactly (K = 5, K = None, radius = 1.0 / 1.5 / 2.0 voxels)"""
+  from gcl_b200 import groups as gg
+  for c, centre, nbs, Ts, radius, K, g in _load_group_cases():
+    grp, idx, fin = gg.colocation_groups(torch.from_numpy(centre).to(G.dev), [torch.from_numpy(x) for x in nbs], Ts, 0.3, radius, K)
+    assert grp.dtype == torch.int64 and idx.dtype == torch.int64 and fin.dtype == torch.bool
+    assert np.array_equal(grp.cpu().numpy(), g[f"c{c}_group"]), c
+    assert np.array_equal(idx.cpu().numpy(), g[f"c{c}_index"]), c
+    assert np.array_equal(fin.cpu().numpy(), g[f"c{c}_finest"]), c
+  # reference return convention + the loss consumes it: torch.split(index, group) (lib/colocation_trainer.py:440-470)
+  c, centre, nbs, Ts, radius, K, g = next(_load_group_cases())
+  lg, li, lf, ld = gg.get_matching_indices_colocation(torch.from_numpy(centre).to(G.dev), [torch.from_numpy(x) for x in nbs], Ts,
+                                                      radius, 0.3, K=K)
+  assert lg == g["c0_group"].tolist() and li == g["c0_index"].tolist() and ld == [] and sum(lf) == len(lg)
+
+
+def test_colocation_groups_edge_cases(G):
+  from gcl_b200 import groups as gg
+  from gcl_b200._lib import GclbError
+  from oracle import groups as og
+  rng = np.random.RandomState(5)
+  # (a) a neighbour cloud far away: every centre is dropped -> empty outputs
+  centre = (rng.randint(-20, 20, (300, 3)) * 0.3 + 0.15).astype(np.float32)
+  centre = np.unique(centre, axis=0)
+  far = centre + np.float32(500.0)
+  grp, idx, fin = gg.colocation_groups(torch.from_numpy(centre).to(G.dev), [torch.from_numpy(far)], [np.eye(4)], 0.3, 0.45, 5)
+  assert grp.numel() == 0 and idx.numel() == 0 and fin.numel() == 0
+  # (b) lattice points: many exactly tied distances -> smallest index first, same as the oracle; negative coordinates;
+  #     a rotated + translated neighbour cloud
+  yaw = 0.4
+  T = np.eye(4); T[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]; T[:3, 3] = [1.0, -2.0, 0.3]
+  nb = ((centre.astype(np.float64) - T[:3, 3]) @ T[:3, :3]).astype(np.float32)          # T^-1 centre
+  import oracle.me_cpu as OME2
+  _, sel = OME2.utils.sparse_quantize(torch.from_numpy(nb) / 0.3, return_index=True)
+  nb = nb[sel.numpy()]
+  # second neighbour cloud: the same lattice seen from a sensor 1.1 cm away (a cloud identical to the centre cloud would make
+  # the finest-neighbour rule compare a float32 norm with the float64 norm of the SAME point: a pure rounding coin toss)
+  shift = np.array([0.011, -0.007, 0.003])
+  nb2 = (centre.astype(np.float64) + shift).astype(np.float32)
+  T2 = np.eye(4); T2[:3, 3] = -shift
+  for K in (3, None):
+    eg, ei, ef = og.colocation_groups(centre, [nb, nb2], [T, T2], 0.45, K)
+    grp, idx, fin = gg.colocation_groups(torch.from_numpy(centre).to(G.dev), [torch.from_numpy(nb), torch.from_numpy(nb2)],
+                                         [T, T2], 0.3, 0.45, K)
+    assert np.array_equal(grp.cpu().numpy(), eg) and np.array_equal(idx.cpu().numpy(), ei) and np.array_equal(fin.cpu().numpy(), ef)
+  # (c) two points in one voxel is not a loader cloud: refused loudly
+  dup = np.concatenate([centre, centre[:1] + np.float32(0.01)])
+  with pytest.raises(GclbError):
+    gg.colocation_groups(torch.from_numpy(dup).to(G.dev), [torch.from_numpy(nb)], [T], 0.3, 0.45, 5)

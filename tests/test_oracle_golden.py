@@ -55,3 +55,25 @@ def test_exhaustive_hash_symmetry():
   h = oloss.exhaustive_hash([[3, 7, 9], [1, 2]], 100)
   assert sorted(h.tolist()) == sorted([3 * 100 + 7, 3 * 100 + 9, 7 * 100 + 9, 1 * 100 + 2])
   assert oloss.neg_hash([7], [3], 100)[0] == oloss.neg_hash([3], [7], 100)[0] == 307
+
+
+def _group_cases():
+  g = np.load(os.path.join(GOLD, "groups.npz"))
+  for c in range(4):
+    nbs, Ts, j = [], [], 0
+    while f"c{c}_nb{j}" in g:
+      nbs.append(g[f"c{c}_nb{j}"]); Ts.append(g[f"c{c}_T{j}"]); j += 1
+    K = int(g[f"c{c}_K"])
+    yield c, g[f"c{c}_centre"], nbs, Ts, float(g[f"c{c}_radius"]), (None if K < 0 else K), g
+
+
+def test_colocation_groups_match_reference_function():
+  """oracle/groups.py against the fixture produced by the reference's own get_matching_indices_colocation /
+  get_matching_indices (util/pointcloud.py:53-132) -- see tests/golden/make_golden_groups.py for what is pinned"""
+  from oracle import groups as og
+  for c, centre, nbs, Ts, radius, K, g in _group_cases():
+    grp, idx, fin = og.colocation_groups(centre, nbs, Ts, radius, K)
+    assert np.array_equal(grp, g[f"c{c}_group"]) and np.array_equal(idx, g[f"c{c}_index"]) and np.array_equal(fin, g[f"c{c}_finest"])
+    assert fin.sum() == len(grp) and grp.sum() == len(idx)
+    if c == 0:
+      assert np.array_equal(og.matching_indices(nbs[0], centre, Ts[0], radius, K), g[f"c{c}_pairs"])
