@@ -35,6 +35,8 @@ SIGNATURES = {
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,
                                         _p, _p, _p, _p, _p]),
     "gclb_groups_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gclb_exhaustive_hash_workspace_bytes": (_sz, [_i64]),
+    "gclb_exhaustive_hash": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     "gclb_colocation_groups": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i32, C.c_float, C.c_double, _i32, _i32,
                                          _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_weights_to_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),

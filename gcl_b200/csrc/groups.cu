@@ -204,6 +204,40 @@ __global__ void __launch_bounds__(kCompactBlock) group_scatter_kernel(const int3
   }
 }
 
+// ---- _exhaustive_hash (util/misc.py:29-36): symmetric keys min(a + b*M, a*M + b) of every unordered pair inside a group,
+// in the reference's order (group by group, i ascending, then the members after i).  Thread per group: pair counts ->
+// ordered scan -> write.
+__global__ void __launch_bounds__(kCompactBlock) pair_block_sums_kernel(const int64_t* __restrict__ group_ptr, int64_t G,
+                                                                        int32_t* sums) {
+  __shared__ int total;
+  const int64_t g = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  int c = 0;
+  if (g < G) {
+    const int64_t n = group_ptr[g + 1] - group_ptr[g];
+    c = (int)(n * (n - 1) / 2);
+  }
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kCompactBlock) pair_hash_kernel(const int64_t* __restrict__ group_ptr,
+                                                                  const int64_t* __restrict__ index, int64_t G, int64_t M,
+                                                                  const int32_t* __restrict__ block_off, int64_t* out) {
+  __shared__ int total;
+  const int64_t g = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  int64_t b = 0, n = 0;
+  if (g < G) { b = group_ptr[g]; n = group_ptr[g + 1] - b; }
+  int64_t pos = block_off[blockIdx.x] + block_exclusive_scan((int)(n * (n - 1) / 2), &total);
+  for (int64_t i = 0; i + 1 < n; ++i) {
+    const int64_t a = index[b + i];
+    for (int64_t j = i + 1; j < n; ++j) {
+      const int64_t c = index[b + j];
+      const int64_t k1 = a + c * M, k2 = a * M + c;
+      out[pos++] = k1 < k2 ? k1 : k2;
+    }
+  }
+}
+
 }  // namespace gclb
 
 using namespace gclb;
@@ -256,6 +290,28 @@ int gclb_colocation_groups(const float* center_xyz, int64_t n_center, const void
   group_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(tmp_size, tmp_finest, tmp_list, L, n_center, sum_len, sum_cnt,
                                                                group_out, index_out, finest_out);
   count_launches(5);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+size_t gclb_exhaustive_hash_workspace_bytes(int64_t n_groups) { return (size_t)(compact_blocks(n_groups) + 8) * 4; }
+
+int gclb_exhaustive_hash(const int64_t* group_ptr, const int64_t* index, int64_t n_groups, int64_t M, int64_t* keys_out,
+                         int64_t* n_keys_out, void* workspace, void* stream) {
+  GCLB_CHECK_ARG(n_keys_out && workspace && (n_groups == 0 || (group_ptr && index && keys_out)), "null pointer");
+  GCLB_CHECK_ARG(M >= 1, "M must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_groups == 0) {
+    cudaMemsetAsync(n_keys_out, 0, 8, st);
+    GCLB_CHECK_LAUNCH();
+    return GCLB_OK;
+  }
+  const int64_t nb = compact_blocks(n_groups);
+  int32_t* sums = (int32_t*)workspace;
+  pair_block_sums_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(group_ptr, n_groups, sums);
+  launch_scan_block_counts(sums, nb, n_keys_out, st);
+  pair_hash_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(group_ptr, index, n_groups, M, sums, keys_out);
+  count_launches(3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
 }

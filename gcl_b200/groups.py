@@ -57,3 +57,23 @@ def get_matching_indices_colocation(center_xyz, neighbourhood_xyz, list_trans, s
   (group, index, finest_flag, central_distance=[])"""
   g, i, f = colocation_groups(center_xyz, neighbourhood_xyz, list_trans, voxel_size, search_voxel_size, K)
   return g.tolist(), i.tolist(), f.float().tolist(), []
+
+
+def exhaustive_hash(group: torch.Tensor, index: torch.Tensor, M: int) -> torch.Tensor:
+  """util/misc.py:29-36 `_exhaustive_hash(torch.split(index, group), M)` on the device: int64 keys of every unordered pair
+  inside a group, reference order.  group int64 [G] sizes, index int64 [sum group] (device)."""
+  dev = index.device
+  assert dev.type == "cuda", "gcl_b200 has no CPU path"
+  group = group.to(device=dev, dtype=torch.int64)
+  index = index.to(torch.int64).contiguous()
+  G = group.numel()
+  gptr = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+  if G:
+    gptr[1:] = torch.cumsum(group, 0)
+  n_keys = int((group * (group - 1) // 2).sum().item()) if G else 0
+  keys = torch.empty(max(n_keys, 1), dtype=torch.int64, device=dev)
+  n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+  lib = _lib.load()
+  ws = torch.empty(max(int(lib.gclb_exhaustive_hash_workspace_bytes(G)), 8), dtype=torch.uint8, device=dev)
+  call("gclb_exhaustive_hash", ptr(gptr), ptr(index), G, int(M), ptr(keys), ptr(n_out), ptr(ws), stream())
+  return keys[:n_keys]

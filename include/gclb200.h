@@ -301,6 +301,13 @@ int gclb_colocation_groups(const float* center_xyz, int64_t n_center, const void
                            int32_t K, int32_t kcap, int64_t* group_out, int64_t* index_out, uint8_t* finest_out,
                            int64_t* n_groups_out, int64_t* n_index_out, int32_t* status, void* workspace, void* stream);
 
+/* _exhaustive_hash (util/misc.py:29-36): for every group (members index[group_ptr[g] .. group_ptr[g+1])) the symmetric keys
+ * min(a + b*M, a*M + b) of all unordered member pairs, in the reference's order; keys_out int64 [sum n_g (n_g - 1) / 2]
+ * (the caller sizes it from the group sizes), n_keys_out int64 [1] (device).  Feeds gclb_group_loss's positive-pair filter. */
+size_t gclb_exhaustive_hash_workspace_bytes(int64_t n_groups);
+int gclb_exhaustive_hash(const int64_t* group_ptr, const int64_t* index, int64_t n_groups, int64_t M, int64_t* keys_out,
+                         int64_t* n_keys_out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

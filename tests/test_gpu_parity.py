@@ -783,3 +783,17 @@ def test_colocation_groups_edge_cases(G):
   dup = np.concatenate([centre, centre[:1] + np.float32(0.01)])
   with pytest.raises(GclbError):
     gg.colocation_groups(torch.from_numpy(dup).to(G.dev), [torch.from_numpy(nb)], [T], 0.3, 0.45, 5)
+
+
+def test_exhaustive_hash_vs_reference_order(G):
+  """device _exhaustive_hash against the host restatement of util/misc.py:29-36 (same keys, same order), on the groups of
+  the reference fixture and on ragged / size-1 / empty group lists"""
+  from gcl_b200 import groups as gg
+  from gcl_b200.loss import _exhaustive_hash
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "groups.npz"))
+  for grp, idx, M in [(g["c0_group"], g["c0_index"], 12345), (np.array([1, 4, 2, 1, 7]), np.arange(15)[::-1].copy(), 50),
+                      (np.zeros(0, np.int64), np.zeros(0, np.int64), 10)]:
+    split = np.split(idx, np.cumsum(grp)[:-1]) if len(grp) else []
+    want = _exhaustive_hash(split, M)
+    got = gg.exhaustive_hash(torch.from_numpy(np.asarray(grp, np.int64)).to(G.dev), torch.from_numpy(np.asarray(idx, np.int64)).to(G.dev), M)
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
