@@ -77,3 +77,14 @@ def test_colocation_groups_match_reference_function():
     assert fin.sum() == len(grp) and grp.sum() == len(idx)
     if c == 0:
       assert np.array_equal(og.matching_indices(nbs[0], centre, Ts[0], radius, K), g[f"c{c}_pairs"])
+
+
+def test_sc2pcr_restatement_matches_reference_matcher():
+  """oracle/sc2pcr.py (the next row to be built) against the transforms the reference's own Matcher.SC2_PCR
+  produced on CPU (tests/golden/make_golden_sc2pcr.py), and against the ground-truth motion of the synthetic correspondences"""
+  from oracle import sc2pcr as osc
+  g = np.load(os.path.join(GOLD, "sc2pcr.npz"))
+  for c in range(3):
+    T = osc.sc2_pcr(torch.from_numpy(g[f"c{c}_src"])[None], torch.from_numpy(g[f"c{c}_tgt"])[None])[0].numpy()
+    assert np.abs(T - g[f"c{c}_trans"]).max() < 1e-4
+    assert np.abs(T - g[f"c{c}_gt"]).max() < 1e-2
