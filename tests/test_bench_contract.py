@@ -1,0 +1,32 @@
+"""bench.py contract, CPU side: the reference arm (`--impl reference`, the oracle timed on the host cores) must run without a
+GPU and print ONE JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                     capture_output=True, text=True, timeout=600, cwd=ROOT)
+  assert r.returncode == 0, r.stderr[-2000:]
+  lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d["impl"] == "reference" and d["metric"] == "scan_pairs_per_sec" and d["unit"] == "pairs/s"
+  assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+  assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+  assert "workload" in d["config"] and "model" not in d["config"]
+  cb = d["cpu_baseline"]
+  assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+  e = d["e2e"]
+  assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_non_zero_rank_of_the_reference_arm_exits_quietly():
+  env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                      "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+  assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
