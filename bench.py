@@ -321,6 +321,7 @@ def main():
     # the only difference to the e2e region is that the points are already resident
     pp = out["pair_ptr"].cpu()
     out["pairs"][:int(pp[-1])].cpu()
+    matcher.check(out)                             # fp16-range status word of this batch (4 bytes)
     return out["n_voxels_total"]
 
   d2h_bytes = [0]
@@ -332,7 +333,8 @@ def main():
     pp = out["pair_ptr"].cpu()                     # D2H: correspondences of every pair
     k = int(pp[-1])
     pairs = out["pairs"][:k].cpu()
-    d2h_bytes[0] = pairs.numel() * 8 + pp.numel() * 8
+    matcher.check(out)
+    d2h_bytes[0] = pairs.numel() * 8 + pp.numel() * 8 + 4
     return out["n_voxels_total"]
 
   clocks = ClockSampler(local_rank)      # NVML initialised before anything is timed

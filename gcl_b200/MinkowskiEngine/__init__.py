@@ -309,7 +309,9 @@ class _ConvBase(nn.Module):
 
   def reset_parameters(self):
     with torch.no_grad():
-      stdv = 1.0 / np.sqrt(self.in_channels * self.kernel_volume)
+      # ME 0.5: fan = (out_channels if transposed else in_channels) * kernel_volume
+      fan = (self.out_channels if self.TRANSPOSED else self.in_channels) * self.kernel_volume
+      stdv = 1.0 / np.sqrt(fan)
       self.kernel.uniform_(-stdv, stdv)
       if self.bias is not None:
         self.bias.uniform_(-stdv, stdv)

@@ -32,6 +32,8 @@ SIGNATURES = {
     "gclb_kmap_sort_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_spconv_fwd": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64,
                                   _i32, _p]),
+    "gclb_spconv_set_range_monitor": (C.c_int, [_p]),
+    "gclb_range_check": (C.c_int, [_p, _i32, _p, _p]),
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,
                                         _p, _p, _p, _p, _p]),
     "gclb_groups_workspace_bytes": (_sz, [_i64, _i32, _i32]),
@@ -54,6 +56,8 @@ SIGNATURES = {
     "gclb_debug_tma_gather4": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "gclb_group_loss": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _f32, _f32, _f32,
                                   _i32, _p, _p, _p, _p, _p]),
+    "gclb_group_loss_bwd": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _f32, _f32, _f32,
+                                      _i32, _p, _p, _p, _p, _p]),
 }
 
 _lib = None
@@ -105,7 +109,7 @@ def require_cuda(*tensors):
                       f"got a tensor on {t.device}")
 
 
-ST_RANGE, ST_FULL, ST_DUPLICATE = 1, 2, 4
+ST_RANGE, ST_FULL, ST_DUPLICATE, ST_FP16_OVERFLOW, ST_FP16_UNDERFLOW = 1, 2, 4, 8, 16
 
 
 def check_status(status: torch.Tensor, what: str):
@@ -117,3 +121,9 @@ def check_status(status: torch.Tensor, what: str):
     raise GclbError(f"{what}: coordinate hash table full")
   if s & ST_DUPLICATE:
     raise GclbError(f"{what}: duplicate coordinate rows (quantize with ME.utils.sparse_quantize first)")
+  if s & ST_FP16_OVERFLOW:
+    raise GclbError(f"{what}: an activation left the finite fp16 range (|y| > 65504 or NaN) and was saturated -- these "
+                    "weights need fp32 activation storage: ResUNetEngine(model, half=False)")
+  if s & ST_FP16_UNDERFLOW:
+    raise GclbError(f"{what}: a whole activation tensor is below 2^-11 in magnitude (fp16 subnormal range) -- these "
+                    "weights need fp32 activation storage: ResUNetEngine(model, half=False)")

@@ -42,7 +42,20 @@ struct ConvParams {   // sparse-conv forward arguments shared by the fp32 (spcon
   int relu;
   float* out;
   int64_t n_out;
+  uint32_t* range_mon = nullptr;   // fp16-range monitor of this launch (gclb_spconv_set_range_monitor) or NULL
 };
+// range monitor words: [0] flags (bit 0: a value outside the finite fp16 range was produced, NaN included), [1] max |y| as
+// float bits.  Kernels that store fp16 fold every value in before the saturating conversion.
+constexpr uint32_t kHalfMaxBits = 0x477FE000u;   // 65504.0f
+uint32_t* current_range_monitor();                // thread-local (spconv.cu)
+__device__ __forceinline__ void range_mon_flush(uint32_t* mon, uint32_t abs_bits_max) {   // one call per warp
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) abs_bits_max = max(abs_bits_max, __shfl_xor_sync(0xffffffffu, abs_bits_max, m));
+  if ((threadIdx.x & 31) == 0 && abs_bits_max != 0u) {
+    atomicMax(mon + 1, abs_bits_max);
+    if (abs_bits_max > kHalfMaxBits) atomicOr(mon, 1u);
+  }
+}
 
 // ---- packed coordinate keys: [ batch:10 | x:18 | y:18 | z:18 ], biased by 2^17 ---------------------------
 constexpr int kAxisBits = 18;

@@ -27,6 +27,7 @@ struct LossParams {
   const int64_t* keys; int64_t n_keys;
   float pos_t, fin_t, neg_t; int square;
   float w_pos, w_fin, w_neg;
+  const float* w_dev;      // device float[3] (upstream gradients of the three losses) or NULL: use w_pos / w_fin / w_neg
   float* pos_vals; float* fin_vals; float* neg_vals; int32_t* neg_j; float* neg_D;
   float* losses; float* gradF;
 };
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(256) group_pos_kernel(LossParams p) {
   float fin = 0.f, e2 = 0.f, dfin[CPL];
   int64_t fin_row = -1;
   if (p.finest_pos) {
-    fin_row = p.index[b + p.finest_pos[g]];
+    const int fp = p.finest_pos[g];
+    fin_row = p.index[b + ((fp >= 0 && fp < n) ? fp : 0)];     // the host rejects groups without a finest member
     const float* f = p.F + (size_t)fin_row * p.C;
 #pragma unroll
     for (int q = 0; q < CPL; ++q) { int c = lane + 32 * q; dfin[q] = (c < p.C) ? mu[q] - __ldg(f + c) : 0.f; e2 = fmaf(dfin[q], dfin[q], e2); }
@@ -85,9 +87,10 @@ __global__ void __launch_bounds__(256) group_pos_kernel(LossParams p) {
   if (lane == 0) { p.pos_vals[s] = pos; p.fin_vals[s] = fin; }
   if (!p.gradF) return;
 
-  const float gs_pos = (pos > 0.f) ? p.w_pos / (float)p.n_sel : 0.f;
+  const float w_pos = p.w_dev ? __ldg(p.w_dev) : p.w_pos, w_fin = p.w_dev ? __ldg(p.w_dev + 1) : p.w_fin;
+  const float gs_pos = (pos > 0.f) ? w_pos / (float)p.n_sel : 0.f;
   float gs_fin = 0.f;
-  if (p.finest_pos && fin > 0.f) gs_fin = p.w_fin / (float)p.n_sel * (p.square ? 2.f : 1.f / sqrtf(e2 + kEps));
+  if (p.finest_pos && fin > 0.f) gs_fin = w_fin / (float)p.n_sel * (p.square ? 2.f : 1.f / sqrtf(e2 + kEps));
   if (gs_pos == 0.f && gs_fin == 0.f) return;
   for (int64_t m = b; m < e; ++m) {
     const int64_t row = p.index[m];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) hardneg_bwd_kernel(LossParams p) {
   const float h = fmaxf(p.neg_t - D, 0.f);
   if (h == 0.f) return;
   // L = mean relu(t - D)^2 ; dL/dD = -2 h / n_valid ; dD/da = (a - b) / D
-  const float coef = p.w_neg * (-2.f * h) / p.losses[3] / D;
+  const float coef = (p.w_dev ? __ldg(p.w_dev + 2) : p.w_neg) * (-2.f * h) / p.losses[3] / D;
   const int64_t arow = p.sel1[r], brow = p.sel2[j];
   for (int c = lane; c < p.C; c += 32) {
     float d = __ldg(p.F + (size_t)arow * p.C + c) - __ldg(p.F + (size_t)brow * p.C + c);
@@ -203,16 +206,17 @@ extern "C" {
 
 size_t gclb_loss_workspace_bytes(int64_t n_sel, int64_t n_hn) { return (size_t)(2 * n_sel + 3 * n_hn + 16) * 4; }
 
-int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
+static int group_loss_impl(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
                     const int32_t* finest_pos, const int64_t* pos_sel, int64_t n_sel, const int64_t* sel_hn1,
                     const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
                     float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
-                    const float* weights, float* losses_out, float* gradF, void* workspace, void* stream) {
+                    const float* weights, const float* upstream_dev, float* losses_out, float* gradF, void* workspace,
+                    void* stream) {
   GCLB_CHECK_ARG(F && group_ptr && index && pos_sel && sel_hn1 && sel_hn2 && losses_out && workspace, "null pointer");
   GCLB_CHECK_ARG(C >= 1 && C <= kMaxC, "C must be in 1..128");
   GCLB_CHECK_ARG(n_sel >= 1 && n_hn >= 1, "empty selection");
   GCLB_CHECK_ARG(n_keys == 0 || pos_keys_sorted, "null pointer");
-  GCLB_CHECK_ARG(!gradF || weights, "weights are required with gradF");
+  GCLB_CHECK_ARG(!gradF || weights || upstream_dev, "weights (host) or upstream (device) are required with gradF");
   cudaStream_t st = (cudaStream_t)stream;
   LossParams p;
   p.F = F; p.N = N; p.C = C; p.group_ptr = group_ptr; p.index = index; p.finest_pos = finest_pos;
@@ -220,10 +224,8 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
   p.keys = pos_keys_sorted; p.n_keys = n_keys;
   p.pos_t = pos_thresh; p.fin_t = finest_thresh; p.neg_t = neg_thresh; p.square = square_loss;
   p.w_pos = p.w_fin = p.w_neg = 0.f;
-  if (gradF) {
-    // weights is a DEVICE or HOST pointer? -> host: three scalars passed by the binding
-    p.w_pos = weights[0]; p.w_fin = weights[1]; p.w_neg = weights[2];
-  }
+  p.w_dev = gradF ? upstream_dev : nullptr;
+  if (gradF && !upstream_dev) { p.w_pos = weights[0]; p.w_fin = weights[1]; p.w_neg = weights[2]; }   // host scalars
   float* ws = (float*)workspace;
   p.pos_vals = ws; p.fin_vals = ws + n_sel; p.neg_vals = ws + 2 * n_sel;
   p.neg_j = (int32_t*)(ws + 2 * n_sel + n_hn); p.neg_D = ws + 2 * n_sel + 2 * n_hn;
@@ -235,6 +237,27 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
   count_launches(gradF ? 4 : 3);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;
+}
+
+int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
+                    const int32_t* finest_pos, const int64_t* pos_sel, int64_t n_sel, const int64_t* sel_hn1,
+                    const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
+                    float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
+                    const float* weights, float* losses_out, float* gradF, void* workspace, void* stream) {
+  return group_loss_impl(F, N, C, group_ptr, index, finest_pos, pos_sel, n_sel, sel_hn1, sel_hn2, n_hn, pos_keys_sorted,
+                         n_keys, pos_thresh, finest_thresh, neg_thresh, square_loss, weights, nullptr, losses_out, gradF,
+                         workspace, stream);
+}
+
+int gclb_group_loss_bwd(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
+                        const int32_t* finest_pos, const int64_t* pos_sel, int64_t n_sel, const int64_t* sel_hn1,
+                        const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
+                        float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
+                        const float* upstream_dev, float* losses_scratch, float* gradF, void* workspace, void* stream) {
+  GCLB_CHECK_ARG(upstream_dev && gradF && losses_scratch, "null pointer");
+  return group_loss_impl(F, N, C, group_ptr, index, finest_pos, pos_sel, n_sel, sel_hn1, sel_hn2, n_hn, pos_keys_sorted,
+                         n_keys, pos_thresh, finest_thresh, neg_thresh, square_loss, nullptr, upstream_dev, losses_scratch,
+                         gradF, workspace, stream);
 }
 
 }  // extern "C"

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(256, 4) spconv_fwd_probe_small_cin_kernel(Conv
   }
   const int64_t o_first = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5), o_step = (int64_t)gridDim.x * wpb;
   int4 c_next = o_first < p.n_out ? __ldg(reinterpret_cast<const int4*>(coords4) + o_first) : make_int4(0, 0, 0, 0);
+  uint32_t amax_bits = 0u;                        // fp16-range monitor (see common.cuh)
   for (int64_t o = o_first; o < p.n_out; o += o_step) {
     const int4 c = c_next;                        // the next row's coordinates are already in flight
     if (o + o_step < p.n_out) c_next = __ldg(reinterpret_cast<const int4*>(coords4) + o + o_step);
@@ -374,11 +375,14 @@ __global__ void __launch_bounds__(256, 4) spconv_fwd_probe_small_cin_kernel(Conv
         float v = acc[q] * (p.scale ? __ldg(p.scale + n) : 1.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
         if (p.residual) v += __ldg(p.residual + (size_t)o * cout + n);
         v = (p.relu & 1) ? fmaxf(v, 0.f) : v;
-        if (p.relu & 16) reinterpret_cast<__half*>(p.out)[(size_t)o * cout + n] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-        else p.out[(size_t)o * cout + n] = v;
+        if (p.relu & 16) {
+          amax_bits = max(amax_bits, __float_as_uint(v) & 0x7fffffffu);
+          reinterpret_cast<__half*>(p.out)[(size_t)o * cout + n] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        } else p.out[(size_t)o * cout + n] = v;
       }
     }
   }
+  if (p.range_mon && (p.relu & 16)) range_mon_flush(p.range_mon, amax_bits);
 }
 
 template <int BM, int BN, bool VEC>
@@ -485,11 +489,41 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   }
 }
 
+static thread_local uint32_t* g_range_mon = nullptr;
+uint32_t* current_range_monitor() { return g_range_mon; }
+
+// one warp: fold the per-layer monitor words into the caller's status word
+__global__ void range_check_kernel(const uint32_t* __restrict__ mons, int n_layers, int32_t* __restrict__ status) {
+  int bits = 0;
+  for (int l = threadIdx.x; l < n_layers; l += 32) {
+    const uint32_t flags = mons[2 * l], amax = mons[2 * l + 1];
+    if (flags & 1u) bits |= GCLB_ST_FP16_OVERFLOW;
+    // the largest magnitude of a whole tensor sits below 2^-11: its entries are fp16 subnormals or close to it
+    if (amax != 0u && amax < 0x3A000000u) bits |= GCLB_ST_FP16_UNDERFLOW;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, m);
+  if (threadIdx.x == 0 && bits) atomicOr(status, bits);
+}
+
 }  // namespace gclb
 
 using namespace gclb;
 
 extern "C" {
+
+int gclb_spconv_set_range_monitor(uint32_t* mon) {
+  g_range_mon = mon;
+  return GCLB_OK;
+}
+
+int gclb_range_check(const uint32_t* mons, int32_t n_layers, int32_t* status, void* stream) {
+  GCLB_CHECK_ARG(mons && status && n_layers >= 1, "bad arguments");
+  range_check_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mons, n_layers, status);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
 
 int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, int64_t n_in, const void* W_,
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
@@ -517,6 +551,7 @@ int gclb_spconv_fwd(const void* in0_, int32_t c0, const void* in1_, int32_t c1, 
   if (n_out == 0) return GCLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ConvParams p{in0, in1, c0, c1, W, K, cout, nbr, row_perm, tile_mask, scale, shift, residual, relu, out, n_out};
+  p.range_mon = current_range_monitor();
   const int cin = c0 + c1;
   cudaError_t e;
   if (algo == 2) {   // W is in the tensor-core layout [K][cout][cin]
@@ -568,6 +603,7 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
   const size_t smem = (size_t)K * cin * cout * 4;
   GCLB_CHECK_ARG(smem <= 200 * 1024, "weights do not fit in shared memory");
   ConvParams p{in, nullptr, cin, 0, W, K, cout, nullptr, nullptr, nullptr, scale, shift, residual, relu, out, n};
+  p.range_mon = current_range_monitor();
   GCLB_CHECK_ARG(tensor_stride >= 1 && (tensor_stride & (tensor_stride - 1)) == 0, "tensor stride must be a power of two");
   HashTable t = make_table(table, capacity, tensor_stride);
   cudaStream_t st = (cudaStream_t)stream;

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
     // ======================================= epilogue: thread <-> output row ================================
     const int quarter = warp & 3;                      // TMEM lanes this warp may read
     const int row = quarter * 32 + lane;
+    uint32_t amax_bits = 0u;                           // fp16-range monitor: max |y| (float bits; NaN sorts above inf)
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt % NACC;
@@ -311,6 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
             for (int q = 0; q < 32; ++q) y[q] = y[q] / nrm;
           }
           if (out_half) {                               // fp16 activations for the next layer (saturating, round to nearest)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
             __half* dst = reinterpret_cast<__half*>(p.out) + (size_t)o * COUT + n0;
 #pragma unroll
             for (int q = 0; q < 32; q += 8) {
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
         for (int q = 0; q < RV; ++q) rc[q] = rn[q];
       }
     }
+    if (p.range_mon) range_mon_flush(p.range_mon, amax_bits);   // saturation / NaN / tiny tensors are reported, never silent
   }
 
   tc_fence_before();
@@ -443,7 +447,18 @@ using namespace gclb;
 
 extern "C" {
 
-int gclb_has_tcgen05(void) { return 1; }
+int gclb_has_tcgen05(void) {
+  // the tcgen05 / TMEM / TMA kernels exist for sm_100 only: answer for the CURRENT device instead of failing at launch
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (dev == cached_dev) return cached;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cached_dev = dev;
+  cached = (major == 10) ? 1 : 0;
+  return cached;
+}
 
 int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream) {
   GCLB_CHECK_ARG(W && Wt && K >= 1 && cin >= 1 && cout >= 1, "bad arguments");

@@ -13,7 +13,7 @@ from typing import List, Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def _fold(conv, norm, device):
@@ -80,6 +80,12 @@ class ResUNetEngine:
     self.W2 = model.final.kernel.detach().to(d).float().contiguous()
     self.bias = model.final.bias.detach().to(d).float().reshape(-1).contiguous() if model.final.bias is not None else None
     self.last_maps = None
+    # fp16-range monitor: one (flags, max |y|) pair per fp16-storing launch of a forward + a status word that check_range()
+    # reads (the reference computes in fp32; saturation or a tensor sunk into the fp16 subnormals must not be silent)
+    self.monitor_range = True
+    self.range_status = None
+    self._mon = None
+    self._mon_i = 0
 
     # tensor-core weight copies ([K, Cout, Cin], tf32-rounded) for every layer the tcgen05 kernel covers
     self.tc = {}
@@ -95,7 +101,7 @@ class ResUNetEngine:
         c0 = self.SPLIT.get(key, cin)
         if ops.tc_supported(c0, cin - c0, cout, K):
           self.tc[key] = ops.weights_to_tc(W)
-        if self.half and ops.tc_supported(c0, cin - c0, cout, K, half=True):
+        if self.half and ops.tc_supported(c0, cin - c0, cout, K, half=True) and self._fits_fp16(W):
           self.tc16[key] = ops.weights_to_tc(W, half=True, c0=c0)
       # pointwise tail on the tensor cores: [y1 | s1] W1 -> ReLU -> W2 + bias -> L2 normalise (fused in the epilogue)
       c_s1 = type(model).CHANNELS[1]
@@ -103,10 +109,17 @@ class ResUNetEngine:
       self.tail_tc = None
       if (ops.tc_supported(c_y1, c_s1, self.W1.shape[1], 1) and ops.tc_supported(self.W2.shape[0], 0, self.W2.shape[1], 1)
           and self.W2.shape[1] == 32):
-        if self.half:
+        if self.half and self._fits_fp16(self.W1) and self._fits_fp16(self.W2):
           self.tail_tc = (ops.weights_to_tc(self.W1, half=True, c0=c_y1), ops.weights_to_tc(self.W2, half=True))
         else:
           self.tail_tc = (ops.weights_to_tc(self.W1), ops.weights_to_tc(self.W2))
+
+  @staticmethod
+  def _fits_fp16(W) -> bool:
+    """construction-time guard for the fp16 weight images (the conversion saturates): a layer whose weights leave the fp16
+    range, or sit wholly below 2^-11, keeps fp32 weights and runs on the kind::tf32 path instead"""
+    a = float(W.abs().max())
+    return a <= 65504.0 and (a == 0.0 or a >= 2.0 ** -11)
 
   # first-source channel count of the layers that read a concatenation (ME.cat fused into the gather)
   SPLIT = {}
@@ -116,9 +129,43 @@ class ResUNetEngine:
     """storage dtype a layer reads its inputs in"""
     return torch.float16 if key in self.tc16 else torch.float32
 
+  MAX_MONITORS = 32
+
+  def _mon_begin(self, device):
+    if not (self.half and self.monitor_range):
+      self._mon = None
+      return
+    buf = torch.zeros(2 * self.MAX_MONITORS + 1, dtype=torch.int32, device=device)   # monitors + the status word
+    self._mon, self.range_status, self._mon_i = buf, buf[2 * self.MAX_MONITORS:], 0
+
+  def _mon_next(self, out_dtype):
+    """arm the thread-local monitor pointer for the next launch when it stores fp16"""
+    if self._mon is None:
+      return
+    if out_dtype == torch.float16:
+      assert self._mon_i < self.MAX_MONITORS
+      _lib.call("gclb_spconv_set_range_monitor", self._mon.data_ptr() + 8 * self._mon_i)
+      self._mon_i += 1
+    else:
+      _lib.call("gclb_spconv_set_range_monitor", None)
+
+  def _mon_end(self):
+    if self._mon is None:
+      return
+    _lib.call("gclb_spconv_set_range_monitor", None)
+    if self._mon_i:
+      _lib.call("gclb_range_check", self._mon.data_ptr(), self._mon_i, self.range_status.data_ptr(), _lib.stream())
+
+  def check_range(self):
+    """one host read: raise GclbError if the last forward saturated an fp16 activation or produced a tensor in the fp16
+    subnormal range (the pipeline folds this word into the read-back it does anyway)"""
+    if self.range_status is not None:
+      _lib.check_status(self.range_status, "ResUNetEngine forward (fp16 activations)")
+
   def _conv(self, key, x, nbr, n_out, x2=None, residual=None, relu=False, out_dtype=torch.float32):
     W, sc, sh = self.p[key]
     dt = self._want(key)
+    self._mon_next(out_dtype if key in self.tc else None)
     # no-ops on the tuned path (every producer already writes what its consumer reads); a model variant whose channel
     # widths mix eligible and ineligible layers converts here
     x = x if x.dtype == dt else x.to(dt)
@@ -219,9 +266,11 @@ class ResUNetEngine:
     self.last_maps = (cms, km)
     n1, n2, n4, n8 = cms[1].n, cms[2].n, cms[4].n, cms[8].n
     x = feats.contiguous().float()
+    self._mon_begin(x.device)
     if self.conv1_probe:
       W, sc, sh = self.p["conv1"]
       od = self._want("block1.1")
+      self._mon_next(od)
       if "k3s1" in km:
         c1 = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, out_dtype=od)
       else:   # conv1's inner probes are the stride-1 3x3x3 kernel map: emitted by the same kernel, bucketed here
@@ -246,9 +295,12 @@ class ResUNetEngine:
                      tail_dt)
     s1 = s1 if s1.dtype == tail_dt else s1.to(tail_dt)        # no-op on the tuned path
     if getattr(self, "tail_tc", None) is not None:
+      self._mon_next(y1.dtype)
       h = ops.spconv_fwd(y1, self.tail_tc[0], None, n1, in1=s1, relu=True, algo=2)
+      self._mon_end()
       return ops.spconv_fwd(h, self.tail_tc[1], None, n1, shift=self.bias, normalize=self.normalize, algo=2,
                             out_dtype=torch.float32)
+    self._mon_end()
     return ops.pointwise_tail(y1, s1, self.W1, self.W2, self.bias, normalize=self.normalize)
 
   @torch.no_grad()

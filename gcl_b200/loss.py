@@ -5,10 +5,10 @@ Mirrors /root/reference/lib/colocation_trainer.py:
   location_contrastive_loss  :734-809   (no finest term, non-squared positive term)
 Same arguments and return value `(pos_loss, finest_loss, neg_loss)`; the host-side random selections are drawn
 with the same `np.random` calls in the same order as the reference (:456-459, :506-507), so a seeded run picks
-the same groups / rows.  Forward AND backward run in one C-ABI call; the three returned scalars are autograd
-leaves of a custom Function whose backward hands out the pre-computed dL/dF, so
-`(pos_w * pos + finest_w * finest + neg_w * neg).backward()` (:878-879) works unchanged -- provided the weights
-are given to the constructor (the kernel needs them when it builds the gradient).
+the same groups / rows.  The three returned scalars are outputs of a custom autograd Function whose backward runs the
+fused gradient kernels with the upstream gradients autograd hands it (device scalars, no host read), so the trainer's
+`pos_loss /= iter_size ... (pos_w * pos + finest_w * finest + neg_w * neg).backward()` (:874-879) works unchanged for
+any weights / scaling; the constructor's `*_weight` arguments are kept for API compatibility and are not needed.
 """
 from __future__ import annotations
 
@@ -30,30 +30,46 @@ def _exhaustive_hash(index_split, M):
 
 
 class _GroupLossFn(torch.autograd.Function):
+  """forward: gclb_group_loss (forward only); backward: gclb_group_loss_bwd with the ACTUAL upstream gradients of the
+  three losses, handed to the kernels as a device float[3] (no host read).  Any scaling of the losses before
+  `.backward()` -- the reference's `loss / iter_size` (lib/colocation_trainer.py:874-878), AMP loss scaling, using only
+  one of the terms -- therefore back-propagates correctly."""
+
   @staticmethod
   def forward(ctx, F_out, args):
-    (group_ptr, index, finest_pos, pos_sel, sel1, sel2, keys, thr, square, weights) = args
+    (group_ptr, index, finest_pos, pos_sel, sel1, sel2, keys, thr, square) = args
     F_c = F_out.detach().contiguous().float()
     N, Cd = F_c.shape
     dev = F_c.device
     lib = _lib.load()
     losses = torch.empty(4, dtype=torch.float32, device=dev)
-    need_grad = F_out.requires_grad
-    grad = torch.zeros_like(F_c) if need_grad else None
     ws = torch.empty(int(lib.gclb_loss_workspace_bytes(pos_sel.numel(), sel1.numel())), dtype=torch.uint8, device=dev)
-    w = (_lib.C.c_float * 3)(*weights)
     call("gclb_group_loss", ptr(F_c), N, Cd, ptr(group_ptr), ptr(index), ptr(finest_pos), ptr(pos_sel),
          pos_sel.numel(), ptr(sel1), ptr(sel2), sel1.numel(), ptr(keys), keys.numel(), thr[0], thr[1], thr[2],
-         int(square), _lib.C.cast(w, _lib.C.c_void_p), ptr(losses), ptr(grad), ptr(ws), stream())
-    ctx.grad = grad
-    ctx.weights = weights
-    return losses[0], losses[1], losses[2]
+         int(square), None, ptr(losses), None, ptr(ws), stream())
+    ctx.save_for_backward(F_c)
+    ctx.args = args
+    # three separately owned 0-d tensors (not views of one buffer): the reference divides them in place
+    # (`pos_loss /= iter_size`, :874-876), which autograd forbids on views returned by a multi-output Function
+    pos, fin, neg = losses[0].clone(), losses[1].clone(), losses[2].clone()
+    return pos, fin, neg
 
   @staticmethod
   def backward(ctx, g_pos, g_fin, g_neg):
-    # dL/dF was built for L = sum_i w_i * loss_i; the incoming grads must be exactly those weights
-    # (checked on the host only in debug mode to avoid a sync)
-    return ctx.grad, None
+    (F_c,) = ctx.saved_tensors
+    (group_ptr, index, finest_pos, pos_sel, sel1, sel2, keys, thr, square) = ctx.args
+    dev = F_c.device
+    z = torch.zeros((), dtype=torch.float32, device=dev)
+    up = torch.stack([(g if g is not None else z).to(torch.float32).reshape(()) for g in (g_pos, g_fin, g_neg)]).contiguous()
+    N, Cd = F_c.shape
+    lib = _lib.load()
+    grad = torch.zeros_like(F_c)
+    scratch = torch.empty(4, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(lib.gclb_loss_workspace_bytes(pos_sel.numel(), sel1.numel())), dtype=torch.uint8, device=dev)
+    call("gclb_group_loss_bwd", ptr(F_c), N, Cd, ptr(group_ptr), ptr(index), ptr(finest_pos), ptr(pos_sel),
+         pos_sel.numel(), ptr(sel1), ptr(sel2), sel1.numel(), ptr(keys), keys.numel(), thr[0], thr[1], thr[2],
+         int(square), ptr(up), ptr(scratch), ptr(grad), ptr(ws), stream())
+    return grad, None
 
 
 class GroupContrastiveLoss:
@@ -86,6 +102,8 @@ class GroupContrastiveLoss:
       sel2 = self.rng.choice(N, min(N, max_hn_samples), replace=False)
     else:
       pos_sel, sel1, sel2 = selections
+    if G == 0 or bool((group_h < 1).any()):
+      raise _lib.GclbError("group sizes must be >= 1 and there must be at least one group")
     group_ptr = torch.zeros(G + 1, dtype=torch.int64)
     group_ptr[1:] = torch.cumsum(group_h, 0)
     index_d = torch.as_tensor(index).to(device=dev, dtype=torch.int64).contiguous()
@@ -97,12 +115,15 @@ class GroupContrastiveLoss:
       big = torch.full((G,), 1 << 30, dtype=torch.int64)
       gid = torch.repeat_interleave(torch.arange(G), group_h)
       big.scatter_reduce_(0, gid[ff], pos_in_group[ff], reduce="amin")
-      finest_pos = big.to(torch.int32).to(dev)
+      sel_groups = torch.as_tensor(np.asarray(pos_sel), dtype=torch.int64)
+      if bool((big[sel_groups] >= (1 << 30)).any()):
+        # the reference raises IndexError here (`feature_set[finest_flag_set][0]` on an empty selection, :484)
+        raise _lib.GclbError("finest_contrastive_loss: a selected group has no member with finest_flag set")
+      finest_pos = big.clamp_(max=(1 << 30) - 1).to(torch.int32).to(dev)
     keys = torch.sort(torch.as_tensor(np.asarray(index_hash), dtype=torch.int64).to(dev)).values.contiguous()
     to_d = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64).to(dev).contiguous()
     args = (group_ptr.to(dev), index_d, finest_pos, to_d(pos_sel), to_d(sel1), to_d(sel2), keys,
-            (self.pos_thresh, self.finest_thresh, self.neg_thresh), square,
-            self.weights if with_finest else (self.weights[0], 0.0, self.weights[2]))
+            (self.pos_thresh, self.finest_thresh, self.neg_thresh), square)
     return _GroupLossFn.apply(F_out, args)
 
   def finest_contrastive_loss(self, F_out, group, index, index_hash, finest_flag, max_pos_cluster=256,

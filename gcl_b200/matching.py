@@ -6,6 +6,8 @@ Same names, arguments and return conventions as the reference helpers they repla
   find_corr     /root/reference/scripts/test_kitti.py:29-43
   mutual_nn     /root/reference/generalization_ETH/evaluate.py:63-77 (calculate_M): [K,2] (i, nn01[i]) with
                 nn10[nn01[i]] == i, ascending i
+  match_pair    /root/reference/scripts/SC2_PCR/SC2_PCR.py:276-302 (Matcher.match_pair): putative correspondences
+                [1,N,3] x 2 for the SC2-PCR registration
 The N x M matrix is never materialised and there is one device->host copy per call instead of one per chunk.
 """
 from __future__ import annotations
@@ -80,3 +82,24 @@ def find_corr(xyz0, xyz1, F0, F1, subsample_size=-1, rng=np.random):
   if subsample_size > 0 and subsample:
     return xyz0[inds0], xyz1[inds1[nn_inds]]
   return xyz0, xyz1[nn_inds]
+
+
+def match_pair(src_keypts, tgt_keypts, src_features, tgt_features, num_node="all", rng=np.random):
+  """Matcher.match_pair (scripts/SC2_PCR/SC2_PCR.py:276-302): for every (optionally sub-sampled) source keypoint the
+  target keypoint whose descriptor minimises `sqrt(2 - 2 * F0 @ F1.T + 1e-6)`.
+  Inputs carry the reference's leading batch dimension of 1: keypts [1,N,3], features [1,N,C]; returns
+  (src_keypts_corr [1,N,3], tgt_keypts_corr [1,N,3]) on the device.
+  The reference's distance is a monotone function of -F0.F1; on the UNIT-NORM descriptors this path produces
+  (model/resunet.py:226-230; SC2-PCR is only ever fed normalised FCGF features) that is the squared-L2 ordering the
+  fused K4 kernel computes, so no N x M matrix is built; ties / near-ties resolve to the smaller index."""
+  ops.require_cuda(src_keypts, tgt_keypts, src_features, tgt_features)
+  if src_features.dim() != 3 or src_features.shape[0] != 1 or tgt_features.shape[0] != 1:
+    raise GclbError("match_pair expects a leading batch dimension of 1 like the reference (bs == 1)")
+  n_src, n_tgt = src_features.shape[1], tgt_features.shape[1]
+  if num_node != "all":      # :282-284 -- note: sampling WITH replacement, like the reference
+    si = torch.as_tensor(rng.choice(n_src, num_node), device=src_features.device)
+    ti = torch.as_tensor(rng.choice(n_tgt, num_node), device=src_features.device)
+    src_keypts, tgt_keypts = src_keypts[:, si], tgt_keypts[:, ti]
+    src_features, tgt_features = src_features[:, si], tgt_features[:, ti]
+  idx, _ = nn_device(src_features[0].contiguous(), tgt_features[0].contiguous())
+  return src_keypts, tgt_keypts[:, idx]

@@ -8,7 +8,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .engine import ResUNetEngine
 
 
@@ -41,7 +41,15 @@ class PairMatcher:
                                                              a_rows=sel[0], b_rows=sel[1], max_n=cap, max_m=cap)
     pairs, pair_ptr = ops.mutual_filter(idx01, idx10, a_dev, b_dev, ws)
     return dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel[0], sel1=sel[1], a_ptr=a_dev, b_ptr=b_dev, idx01=idx01,
-                idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords)
+                idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords,
+                status=self.engine.range_status)
+
+  @staticmethod
+  def check(out):
+    """read the batch's device status word (4 bytes; do it next to the read-back of the correspondences) and raise
+    GclbError if an fp16-stored activation saturated or sank into the subnormal range during this batch's forward"""
+    if out.get("status") is not None:
+      _lib.check_status(out["status"], "PairMatcher.match (fp16 activations)")
 
   def match_many(self, batches, depth: int = 2):
     """Throughput API: iterate over `(xyz, cloud_ptr)` batches and yield `match()` results in order, keeping `depth`
@@ -61,9 +69,18 @@ class PairMatcher:
         ev.record(st)
       pending.append((out, ev))
       if len(pending) >= depth:
-        o, e = pending.pop(0)
-        e.synchronize()
-        yield o
-    for o, e in pending:
-      e.synchronize()
-      yield o
+        yield self._hand_over(pending.pop(0), cur)
+    for item in pending:
+      yield self._hand_over(item, cur)
+
+  @staticmethod
+  def _hand_over(item, consumer_stream):
+    """the result tensors were allocated on a side stream's pool: wait for the batch, then tell the caching allocator
+    that the consumer's stream uses them too, so a later batch on the side stream cannot recycle a block that
+    asynchronous consumer work is still reading"""
+    out, ev = item
+    ev.synchronize()
+    for v in out.values():
+      if isinstance(v, torch.Tensor) and v.is_cuda:
+        v.record_stream(consumer_stream)
+    return out

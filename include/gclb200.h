@@ -35,12 +35,14 @@ extern "C" {
 #define GCLB_ST_RANGE 1      /* a coordinate was outside the packable range */
 #define GCLB_ST_FULL 2       /* hash table full (capacity too small) */
 #define GCLB_ST_DUPLICATE 4  /* gclb_hash_build saw a duplicated coordinate row */
+#define GCLB_ST_FP16_OVERFLOW 8    /* an fp16-stored activation left the finite fp16 range (or was NaN) and was saturated */
+#define GCLB_ST_FP16_UNDERFLOW 16  /* a whole fp16-stored tensor has max |y| < 2^-11: its values are (near-)subnormal in fp16 */
 
 const char* gclb_last_error(void);
 int gclb_version(void);
 /* process-wide count of CUDA kernels this library has enqueued so far (bench.py reports the delta) */
 int64_t gclb_kernel_launches(void);
-/* 1 when the library was built with the tcgen05 (UTCxMMA) convolution / distance kernels */
+/* 1 when the CURRENT CUDA device can run the tcgen05 (UTCxMMA) / TMEM / TMA kernels (compute capability 10.x), else 0 */
 int gclb_has_tcgen05(void);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -178,6 +180,16 @@ int gclb_spconv_fwd(const void* in0, int32_t c0, const void* in1, int32_t c1, in
                     int32_t K, int32_t cout, const int32_t* nbr, const int32_t* row_perm, const uint32_t* tile_mask,
                     const float* scale, const float* shift, const void* residual, int32_t relu_flags, void* out,
                     int64_t n_out, int32_t algo, void* stream);
+/* fp16-range monitor for the kernels that STORE fp16 (flag bit 4): the reference computes in fp32 (no range limit), so a
+ * checkpoint whose activations overflow fp16 (|y| > 65504, saturated by the epilogue) or sink into its subnormals must be
+ * reported, not silently degraded.  `mon` = device uint32[2], caller-zeroed: [0] bit 0 = a value outside the finite fp16 range
+ * (or NaN) was produced, [1] = max |y| of the launch as float bits.  The pointer is THREAD-LOCAL state picked up by the
+ * following gclb_spconv_fwd / gclb_spconv_fwd_probe calls of this thread (NULL switches monitoring off).
+ * gclb_range_check folds n_layers monitors (uint32 [n_layers, 2]) into the caller's status word: GCLB_ST_FP16_OVERFLOW,
+ * GCLB_ST_FP16_UNDERFLOW (0 < max |y| < 2^-11).  The remedy is the fp32-storage engine (kind::tf32). */
+int gclb_spconv_set_range_monitor(uint32_t* mon);
+int gclb_range_check(const uint32_t* mons, int32_t n_layers, int32_t* status, void* stream);
+
 /* stride-1 convolution with a small input width (cin <= 4, e.g. conv1 of ResUNet: cin = 1, kernel 5^3) with the kernel
  * map FUSED into the convolution: the kernel probes the coordinate hash of the (single) coordinate map itself, so no
  * [n, K] neighbour table is built, written or read (model/resunet.py:38-45,174).  Same epilogue as gclb_spconv_fwd
@@ -270,6 +282,17 @@ int gclb_group_loss(const float* F, int64_t N, int32_t C, const int64_t* group_p
                     const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
                     float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
                     const float* weights, float* losses_out, float* gradF, void* workspace, void* stream);
+/* backward of the three losses for ARBITRARY upstream gradients (what autograd hands to the backward of
+ * `(pos_w * pos / iter_size + ...).backward()`, lib/colocation_trainer.py:874-879): same inputs as gclb_group_loss,
+ *   upstream DEVICE float32[3] = dL/d(pos), dL/d(finest), dL/d(neg)  (no host read: the scalars stay on the device)
+ *   gradF device float32 [N, C], caller-zeroed: gradF += sum_i upstream[i] * d loss_i / dF
+ *   losses_scratch device float32[4] (recomputed forward values; the kernels are latency-bound, recomputation is cheaper
+ *   than keeping per-term gradient planes) */
+int gclb_group_loss_bwd(const float* F, int64_t N, int32_t C, const int64_t* group_ptr, const int64_t* index,
+                        const int32_t* finest_pos, const int64_t* pos_sel, int64_t n_sel, const int64_t* sel_hn1,
+                        const int64_t* sel_hn2, int64_t n_hn, const int64_t* pos_keys_sorted, int64_t n_keys,
+                        float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
+                        const float* upstream, float* losses_scratch, float* gradF, void* workspace, void* stream);
 
 /* bring-up helper (not on the hot path): one TMA tile::gather4 of rows rows4_host[0..3] x channels [col, col+32) of the
  * fp32 matrix X [n, c] into a SWIZZLE_128B shared-memory tile, dumped to out256 (device, 256 floats). */

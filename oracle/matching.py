@@ -5,6 +5,7 @@ Restates, in torch-CPU / numpy:
   find_nn_gpu    /root/reference/lib/eval.py:18-48         (chunks of nn_max_n rows, min over dim 1)
   calculate_M    /root/reference/generalization_ETH/evaluate.py:63-77   (mutual NN, ascending i)
   find_corr      /root/reference/scripts/test_kitti.py:29-43
+  match_pair     /root/reference/scripts/SC2_PCR/SC2_PCR.py:276-302 (literal formula: sqrt(2 - 2 F0 F1^T + 1e-6), argmin)
 Pinned against the reference's own functions imported in the build container
 (tests/test_oracle_vs_reference_py.py; golden vectors tests/golden/nn_*.npz, generator tests/golden/make_golden.py).
 """
@@ -68,3 +69,11 @@ def find_corr(xyz0, xyz1, F0, F1, subsample_size=-1, rng=np.random):
   if subsample_size > 0 and subsample:
     return xyz0[inds0], xyz1[inds1[nn_inds]]
   return xyz0, xyz1[nn_inds]
+
+
+def match_pair(src_keypts, tgt_keypts, src_features, tgt_features):
+  """scripts/SC2_PCR/SC2_PCR.py:276-302 with num_node == 'all' (inputs [1,N,3] / [1,N,C]).
+  Returns (src_keypts_corr, tgt_keypts_corr, source_idx)."""
+  distance = torch.sqrt(2 - 2 * (src_features[0] @ tgt_features[0].T) + 1e-6)
+  source_idx = torch.argmin(distance, dim=1)
+  return src_keypts, tgt_keypts[:, source_idx], source_idx

@@ -63,7 +63,7 @@ def nn_fixture():
 
 
 def loss_fixture():
-  (ct,) = import_reference(OME, ("lib.colocation_trainer",))
+  ct, misc = import_reference(OME, ("lib.colocation_trainer", "util.misc"))
   rng = np.random.RandomState(11)
   N, G, C = 3000, 500, 32
   F = rng.randn(N, C).astype(np.float32)
@@ -76,7 +76,9 @@ def loss_fixture():
     m = index[starts[g]:starts[g + 1]]
     F[m] = F[m[0]] + 0.3 * rng.rand() * rng.randn(len(m), C).astype(np.float32)
   F /= np.linalg.norm(F, axis=1, keepdims=True)
-  ih = oloss.exhaustive_hash([index[starts[g]:starts[g + 1]] for g in range(G)], N)
+  # the reference's own util/misc.py:29-36 (what the collate calls), not the oracle restatement
+  ih = misc._exhaustive_hash(torch.split(torch.from_numpy(index), sizes.tolist()), N).astype(np.int64)
+  assert np.array_equal(ih, oloss.exhaustive_hash([index[starts[g]:starts[g + 1]] for g in range(G)], N))
   out = dict(F=F, group=sizes.astype(np.int64), index=index, finest_flag=flag, index_hash=ih)
   for name, square in (("finest_sq", True), ("finest_l2", False), ("location", False)):
     self = types.SimpleNamespace(device=torch.device("cpu"), pos_thresh=0.1, neg_thresh=1.4, finest_thresh=0.2,

@@ -192,3 +192,81 @@ def test_full_size_nn_optimality_and_mutual(G):
   assert len(pairs) > 4000 and bool((np.diff(pairs[:, 0]) > 0).all())
   i, jj = torch.from_numpy(pairs[:, 0]).to(DEV), torch.from_numpy(pairs[:, 1]).to(DEV)
   assert torch.equal(res[2][0][i], jj) and torch.equal(res[2][2][jj], i)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE configurations against the CPU ORACLE directly (round-1 verdict: the full-size tests only compared the CUDA
+# path with itself).  The oracle takes ~1 s per KITTI-shape scan, so these are cheap.  Bars (north_star): coordinates and
+# unique maps bit-exact, features <= 1e-3 relative in Frobenius norm AND per row (descriptors are unit vectors, so the
+# per-row relative error is the norm of the row difference).
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_forward(G, model_name, clouds, voxel=0.3, seed=0):
+  import bench
+  import oracle.me_cpu as OME
+  cs, sels = [], []
+  for x in clouds:
+    t = torch.from_numpy(x)
+    _, sel = OME.utils.sparse_quantize(t / voxel, return_index=True)
+    cs.append(torch.floor(t[sel] / voxel).int())
+    sels.append(sel)
+  C, F = OME.utils.sparse_collate(cs, [torch.ones(len(c), 1) for c in cs])
+  torch.manual_seed(seed)
+  om = G.make_models(OME)[model_name](**bench.MODEL)
+  g = torch.Generator().manual_seed(seed + 1)
+  for mod in om.modules():
+    if isinstance(mod, torch.nn.BatchNorm1d):
+      mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+      mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+      mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+      mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+  om.eval()
+  torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+  with torch.no_grad():
+    ref = om(OME.SparseTensor(F, coordinates=C)).F
+  off = np.cumsum([0] + [len(x) for x in clouds])
+  umap = torch.cat([s + int(off[i]) for i, s in enumerate(sels)])
+  return om, C, umap, ref
+
+
+def _check_engine_vs_oracle(G, model_name, clouds, half=True):
+  om, C, umap_ref, ref = _oracle_forward(G, model_name, clouds)
+  eng = G.engine.ResUNetEngine(om, device=DEV, half=half)
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(DEV)
+  ptr = torch.tensor(np.cumsum([0] + [len(c) for c in clouds]))
+  feats, cm, umap = eng.extract(xyz, 0.3, ptr)
+  assert torch.equal(cm.coords.cpu(), C)                      # voxel coordinates, row order included: bit-exact
+  assert torch.equal(umap.cpu(), umap_ref)                    # unique_map: bit-exact
+  d = feats.cpu() - ref
+  fro = (d.norm() / ref.norm()).item()
+  worst = (d.norm(dim=1) / ref.norm(dim=1)).max().item()
+  print(f"[{model_name} half={half}] V={len(ref)} frobenius {fro:.2e} worst row {worst:.2e}")
+  assert fro < 1e-3, fro
+  assert worst < 1e-3, worst
+  eng.check_range()                                            # no fp16 saturation / underflow flagged
+  return fro, worst
+
+
+def test_kitti_pair_fp16_engine_vs_oracle(G, kitti_pair):
+  """BASELINE config 2 at full size: one LoKITTI-style pair (2 x ~130k points) through the fp16 tcgen05 engine vs the
+  fp32 CPU oracle"""
+  x0, x1, _ = kitti_pair
+  _check_engine_vs_oracle(G, "ResUNetBN2C", [x0, x1])
+
+
+def test_kitti_pair_tf32_engine_vs_oracle(G, kitti_pair):
+  """same with fp32 activation storage (kind::tf32 operands)"""
+  x0, x1, _ = kitti_pair
+  _check_engine_vs_oracle(G, "ResUNetBN2C", [x0[:60000], x1[:60000]], half=False)
+
+
+def test_nuscenes_batch16_engine_vs_oracle(G):
+  """BASELINE config 3: 16 nuScenes-shape clouds (8 pairs) in one batch vs the oracle"""
+  clouds = [G.synth.cast(G.synth.Scene(20 + i // 2), G.synth.NUSCENES, (3.0 * (i % 2), 0.0, 0.02 * i), seed=i) for i in range(16)]
+  _check_engine_vs_oracle(G, "ResUNetBN2C", clouds)
+
+
+def test_resunet_fatbn_engine_vs_oracle(G):
+  """the variant GCL's scripts train / evaluate (scripts/train_gcl_kitti.sh:13, generalization_ETH/evaluate.py:227):
+  128-wide decoder, 160-channel conv1_tr input"""
+  clouds = [G.synth.cast(G.synth.Scene(40 + i), G.synth.NUSCENES, (2.0 * i, 0.0, 0.0), seed=i) for i in range(2)]
+  _check_engine_vs_oracle(G, "ResUNetFatBN", clouds)

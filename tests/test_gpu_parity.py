@@ -465,6 +465,44 @@ def test_resunet_engine_vs_oracle(G, net):
   assert _rel(feats_p, ref[perm]) < FEAT_TOL
 
 
+def test_fp16_activation_range_is_monitored(G, net):
+  """fp16 activation storage (engine default) against magnitudes a real checkpoint could produce: BN scales pushing the
+  activations to ~1e5 (beyond fp16's 65504) or down to ~1e-7 (fp16 subnormals).  The reference computes in fp32 and has
+  no such limit, so the engine must either stay within tolerance or report it loudly -- never saturate silently.  The
+  fp32-storage engine (kind::tf32) handles the same weights within tolerance."""
+  import copy
+  from gcl_b200._lib import GclbError
+  om, clouds, C_ref, F_in, ref = net
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(G.dev)
+  ptr = torch.tensor([0, len(clouds[0]), len(clouds[0]) + len(clouds[1])])
+  eng = G.engine.ResUNetEngine(om, device=G.dev)
+  eng.extract(xyz, 0.3, ptr)
+  eng.check_range()                                   # the seeded model is comfortably inside the fp16 range
+  for factor, what in ((3e5, "fp16 range"), (1e-7, "subnormal")):
+    m = copy.deepcopy(om)
+    with torch.no_grad():            # scale the FIRST layer's BN output: block1 and its residual path see the scaled tensor
+      m.norm1.bn.weight.mul_(factor)
+      m.norm1.bn.bias.mul_(factor)
+    m.eval()
+    with torch.no_grad():
+      want = m(OME.SparseTensor(F_in, coordinates=C_ref)).F
+    assert bool(torch.isfinite(want).all())
+    e16 = G.engine.ResUNetEngine(m, device=G.dev)
+    f16, _, _ = e16.extract(xyz, 0.3, ptr)
+    ok = _rel(f16, want) < FEAT_TOL
+    flagged = False
+    try:
+      e16.check_range()
+    except GclbError as ex:
+      flagged = what in str(ex)
+    assert ok or flagged, f"factor {factor}: fp16 engine is off by {_rel(f16, want):.2e} and did not flag it"
+    assert flagged, f"factor {factor}: activations of magnitude ~{factor} must set the status word"
+    e32 = G.engine.ResUNetEngine(m, device=G.dev, half=False)       # the remedy named in the error message
+    f32, _, _ = e32.extract(xyz, 0.3, ptr)
+    assert _rel(f32, want) < FEAT_TOL
+    e32.check_range()
+
+
 @pytest.mark.parametrize("mode,w,tol", [("fp32", (16, 32, 8), 1e-4), ("tf32", (32, 64, 32), 3e-3)])
 def test_training_step_grads_vs_oracle(G, mode, w, tol):
   """conv dgrad / wgrad (stride-1, strided, transposed, 1x1) and train-mode BN through a small U-shaped net; in 'tf32'
@@ -606,6 +644,34 @@ def test_mutual_nn_and_batched_segments(G):
     assert np.array_equal(got, want)
   single = G.matching.mutual_nn(As[0].numpy(), Bs[0].numpy())
   assert np.array_equal(single, omatch.mutual_nn(As[0], Bs[0])[0])
+
+
+def test_match_pair_vs_oracle(G):
+  """a14: Matcher.match_pair (scripts/SC2_PCR/SC2_PCR.py:276-302) -- the literal `sqrt(2 - 2 F0 F1^T + 1e-6)` arg-min of
+  the oracle against the fused K4 kernel on unit-norm descriptors; rows may differ only where best and second-best dot
+  products are closer than 1e-6 (documented near-ties)"""
+  rng = np.random.RandomState(9)
+  n, m = 3000, 3500
+  F0 = torch.nn.functional.normalize(torch.from_numpy(rng.randn(n, 32).astype(np.float32)), dim=1)
+  F1 = torch.nn.functional.normalize(torch.from_numpy(rng.randn(m, 32).astype(np.float32)), dim=1)
+  F1[:1000] = torch.nn.functional.normalize(F0[:1000] + 0.05 * torch.from_numpy(rng.randn(1000, 32).astype(np.float32)), dim=1)
+  x0 = torch.from_numpy(rng.uniform(-30, 30, (1, n, 3)).astype(np.float32))
+  x1 = torch.from_numpy(rng.uniform(-30, 30, (1, m, 3)).astype(np.float32))
+  s_ref, t_ref, idx_ref = omatch.match_pair(x0, x1, F0[None], F1[None])
+  s, t = G.matching.match_pair(x0.to(G.dev), x1.to(G.dev), F0[None].to(G.dev), F1[None].to(G.dev))
+  assert s.shape == (1, n, 3) and t.shape == (1, n, 3) and torch.equal(s.cpu(), s_ref)
+  same = (t.cpu() == t_ref).all(dim=2)[0]
+  dots = F0 @ F1.T
+  top2 = torch.topk(dots, 2, dim=1).values
+  near_tie = (top2[:, 0] - top2[:, 1]) < 1e-6
+  assert bool((same | near_tie).all()) and same.float().mean().item() > 0.999
+  # sub-sampled variant: same RNG calls as the reference (np.random.choice WITH replacement, src then tgt)
+  r = np.random.RandomState(4)
+  si, ti = r.choice(n, 500), r.choice(m, 500)
+  s_ref2, t_ref2, _ = omatch.match_pair(x0[:, si], x1[:, ti], F0[None][:, si], F1[None][:, ti])
+  s2, t2 = G.matching.match_pair(x0.to(G.dev), x1.to(G.dev), F0[None].to(G.dev), F1[None].to(G.dev), num_node=500,
+                                 rng=np.random.RandomState(4))
+  assert torch.equal(s2.cpu(), s_ref2) and (t2.cpu() == t_ref2).all(dim=2).float().mean().item() > 0.99
 
 
 def test_subsample_is_a_sample_without_replacement(G):
@@ -786,14 +852,61 @@ def test_colocation_groups_edge_cases(G):
 
 
 def test_exhaustive_hash_vs_reference_order(G):
-  """device _exhaustive_hash against the host restatement of util/misc.py:29-36 (same keys, same order), on the groups of
-  the reference fixture and on ragged / size-1 / empty group lists"""
+  """a17: device _exhaustive_hash against (1) keys produced by the reference's own util/misc.py:29-36
+  (tests/golden/pair_hash.npz: same keys, same order) and (2) the ORACLE restatement on ragged / size-1 / empty group lists"""
   from gcl_b200 import groups as gg
-  from gcl_b200.loss import _exhaustive_hash
-  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "groups.npz"))
-  for grp, idx, M in [(g["c0_group"], g["c0_index"], 12345), (np.array([1, 4, 2, 1, 7]), np.arange(15)[::-1].copy(), 50),
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pair_hash.npz"))
+  to_d = lambda a: torch.from_numpy(np.asarray(a, np.int64)).to(G.dev)
+  for c in range(3):
+    got = gg.exhaustive_hash(to_d(g[f"c{c}_group"]), to_d(g[f"c{c}_index"]), int(g[f"c{c}_M"]))
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), g[f"c{c}_keys"]), c
+  rng = np.random.RandomState(3)
+  for grp, idx, M in [(np.array([1, 4, 2, 1, 7]), np.arange(15)[::-1].copy(), 50),
+                      (np.array([3, 1, 1, 9, 2]), rng.randint(0, 10 ** 6, 16), 10 ** 6),
                       (np.zeros(0, np.int64), np.zeros(0, np.int64), 10)]:
     split = np.split(idx, np.cumsum(grp)[:-1]) if len(grp) else []
-    want = _exhaustive_hash(split, M)
-    got = gg.exhaustive_hash(torch.from_numpy(np.asarray(grp, np.int64)).to(G.dev), torch.from_numpy(np.asarray(idx, np.int64)).to(G.dev), M)
+    want = oloss.exhaustive_hash(split, M)
+    got = gg.exhaustive_hash(to_d(grp), to_d(idx), M)
     assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+
+
+def test_group_loss_honours_upstream_gradients(G):
+  """the reference trainer's exact sequence (lib/colocation_trainer.py:874-879): in-place `/= iter_size` on the three
+  returned losses, weighted sum, backward -- with iter_size = 2 and weights that differ from the constructor's; then a
+  backward through ONE term only.  dL/dF must follow autograd's upstream gradients (round-1 bug: they were ignored)."""
+  F, sizes, index, flag, ih = _loss_inputs(11)
+  N = len(F)
+  sel = oloss.draw_selections(len(sizes), N, 512, 1024, np.random.RandomState(0))
+  iter_size, w = 2, (0.3, 1.7, 0.9)
+
+  def run(loss_fn, Fx):
+    pos, fin, neg = loss_fn(Fx)
+    pos /= iter_size          # in place, like the trainer
+    fin /= iter_size
+    neg /= iter_size
+    loss = w[0] * pos + w[1] * fin + w[2] * neg
+    loss.backward()
+    return float(loss)
+
+  Fo = F.clone().requires_grad_(True)
+  lo = run(lambda x: oloss.group_contrastive_loss(x, sizes, index, ih, flag, *sel, square_loss=True, with_finest=True), Fo)
+  crit = G.loss.GroupContrastiveLoss(square_loss=True)          # constructor weights (1, 1, 1) must be irrelevant
+  Fg = F.clone().to(G.dev).requires_grad_(True)
+  lg = run(lambda x: crit.finest_contrastive_loss(x, torch.from_numpy(sizes), torch.from_numpy(index), ih,
+                                                  torch.from_numpy(flag), selections=sel), Fg)
+  assert abs(lg - lo) < 1e-5 * max(1, abs(lo))
+  assert _rel(Fg.grad, Fo.grad) < 1e-4
+  # one term only, scaled: the other two receive no upstream gradient at all
+  Fo2, Fg2 = F.clone().requires_grad_(True), F.clone().to(G.dev).requires_grad_(True)
+  (3.0 * oloss.group_contrastive_loss(Fo2, sizes, index, ih, flag, *sel, square_loss=True, with_finest=True)[2]).backward()
+  (3.0 * crit.finest_contrastive_loss(Fg2, torch.from_numpy(sizes), torch.from_numpy(index), ih, torch.from_numpy(flag),
+                                      selections=sel)[2]).backward()
+  assert _rel(Fg2.grad, Fo2.grad) < 1e-4
+  # a selected group without a finest member: the reference raises IndexError; the product raises instead of reading
+  # out of bounds on the device
+  bad = flag.copy()
+  bad[:sizes[0]] = False
+  from gcl_b200._lib import GclbError
+  with pytest.raises(GclbError):
+    crit.finest_contrastive_loss(Fg2.detach(), torch.from_numpy(sizes), torch.from_numpy(index), ih, torch.from_numpy(bad),
+                                 selections=(np.arange(len(sizes)), sel[1], sel[2]))

@@ -88,3 +88,16 @@ def test_sc2pcr_restatement_matches_reference_matcher():
     T = osc.sc2_pcr(torch.from_numpy(g[f"c{c}_src"])[None], torch.from_numpy(g[f"c{c}_tgt"])[None])[0].numpy()
     assert np.abs(T - g[f"c{c}_trans"]).max() < 1e-4
     assert np.abs(T - g[f"c{c}_gt"]).max() < 1e-2
+
+
+def test_pair_hashes_vs_reference_golden():
+  """a17: oracle restatement of util/misc.py:29-40 against keys produced by the reference's own functions
+  (tests/golden/make_golden_pair_hash.py)"""
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pair_hash.npz"))
+  for c in range(3):
+    grp, idx, M = g[f"c{c}_group"], g[f"c{c}_index"], int(g[f"c{c}_M"])
+    split = np.split(idx, np.cumsum(grp)[:-1])
+    assert np.array_equal(oloss.exhaustive_hash(split, M), g[f"c{c}_keys"])
+  assert np.array_equal(oloss.neg_hash(g["neg_i1"], g["neg_i2"], int(g["neg_M"])), g["neg_keys"])
+  loss = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gcl_loss.npz"))
+  assert np.array_equal(loss["index_hash"], g["c2_keys"])
