@@ -886,7 +886,7 @@ def test_group_loss_honours_upstream_gradients(G):
     neg /= iter_size
     loss = w[0] * pos + w[1] * fin + w[2] * neg
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
   Fo = F.clone().requires_grad_(True)
   lo = run(lambda x: oloss.group_contrastive_loss(x, sizes, index, ih, flag, *sel, square_loss=True, with_finest=True), Fo)
