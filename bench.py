@@ -179,35 +179,47 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
   tabs = {k: (v if isinstance(v, tuple) else (v,)) for k, v in km.items()}
   pair_counts = {k: int((v[0] >= 0).sum().item()) for k, v in tabs.items()}
   recs = []
-  orig = ops.spconv_fwd
+  orig, orig_halo = ops.spconv_fwd, ops.spconv_fwd_halo
+
+  def record(e0, e1, in0, in1, W, out, pairs, residual):
+    K = W.shape[0] if W.dim() == 3 else 1
+    cin, cout, n_out = in0.shape[1] + (in1.shape[1] if in1 is not None else 0), out.shape[1], out.shape[0]
+    # every tensor once at its storage width (fp16 between the layers, fp32 descriptors) + the map + weights
+    alg_bytes = (in0.element_size() * in0.shape[0] * cin + out.element_size() * n_out * cout + 8 * pairs
+                 + W.element_size() * K * cin * cout)
+    if residual is not None:
+      alg_bytes += residual.element_size() * n_out * cout
+    recs.append((e0, e1, alg_bytes, 2 * pairs * cin * cout))
 
   def timed(in0, W, nbr, n_out, in1=None, **kw):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = orig(in0, W, nbr, n_out, in1=in1, **kw)
     e1.record()
-    W3 = W if W.dim() == 3 else W.unsqueeze(0)
-    K, cin, cout = W3.shape
     pairs = n_out if nbr is None else next(pair_counts[k] for k, v in tabs.items() if any(t is nbr for t in v))
-    # every tensor once at its storage width (fp16 between the 64..256-channel layers, fp32 elsewhere) + the map + weights
-    alg_bytes = (in0.element_size() * in0.shape[0] * cin + out.element_size() * n_out * cout + 8 * pairs
-                 + W.element_size() * K * cin * cout)
-    if kw.get("residual") is not None:
-      alg_bytes += kw["residual"].element_size() * n_out * cout
-    recs.append((e0, e1, alg_bytes, 2 * pairs * cin * cout))
+    record(e0, e1, in0, in1, W, out, pairs, kw.get("residual"))
+    return out
+
+  def timed_halo(in0, Wimg, halo, in1=None, **kw):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = orig_halo(in0, Wimg, halo, in1=in1, **kw)
+    e1.record()
+    pairs = next(pair_counts[k] for k, v in tabs.items() if any(t is halo for t in v))
+    record(e0, e1, in0, in1, Wimg, out, pairs, kw.get("residual"))
     return out
 
   feats = torch.ones((cm1.n, 1), device=xyz_dev.device)
   for _ in range(2):  # first pass warms caches, second is recorded
     recs.clear()
-    ops.spconv_fwd = timed
+    ops.spconv_fwd, ops.spconv_fwd_halo = timed, timed_halo
     try:
       # keep the GPU busy for ~10 ms while the host enqueues the whole forward, so that the events bracket back-to-back
       # kernel execution and not the host's launch latency
       torch.cuda._sleep(int(2e7))
       eng.forward(cm1, feats, maps)
     finally:
-      ops.spconv_fwd = orig
+      ops.spconv_fwd, ops.spconv_fwd_halo = orig, orig_halo
   torch.cuda.synchronize()
   ms = [a.elapsed_time(b) for a, b, _, _ in recs]
   tot_ms, tot_b, tot_f = sum(ms), sum(r[2] for r in recs), sum(r[3] for r in recs)

@@ -32,6 +32,11 @@ SIGNATURES = {
     "gclb_kmap_sort_rows": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_spconv_fwd": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64,
                                   _i32, _p]),
+    "gclb_kmap_halo_bytes": (_sz, [_i64]),
+    "gclb_debug_halo_prof": (C.c_int, [_p]),
+    "gclb_kmap_halo_max_groups": (_i32, []),
+    "gclb_kmap_halo_build": (C.c_int, [_p, _i64, _p, _p, _sz, _p, _p, _p, _p, _p]),
+    "gclb_spconv_fwd_halo": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     "gclb_spconv_set_range_monitor": (C.c_int, [_p]),
     "gclb_range_check": (C.c_int, [_p, _i32, _p, _p]),
     "gclb_spconv_fwd_probe": (C.c_int, [_p, _i32, _p, _i32, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _p,

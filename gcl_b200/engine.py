@@ -9,6 +9,7 @@ host synchronisation (the strided-map row counts).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -92,6 +93,7 @@ class ResUNetEngine:
     self.tc16 = {}         # fp16 images of the layers that run with fp16 activations
     self.tail_tc = None
     self.sort_rows = True
+    self.use_halo = os.environ.get("GCLB_HALO", "0") != "0"   # same-map 3x3x3 convolutions on fp16 rows run the halo-staging kernel (csrc/spconv_halo.cu)
     self._side = None      # side streams for overlapped kernel-map construction
     # conv1 with a narrow input: fuse the kernel map into the convolution (no 4*K*N-byte table for the 5^3 kernel)
     self.conv1_probe = (self.p["conv1"][0].shape[1] <= 4 and self.p["conv1"][0].shape[2] <= 128)
@@ -174,8 +176,12 @@ class ResUNetEngine:
     if key in self.tc:
       perm = mask = None
       is_sorted = True
-      if isinstance(nbr, tuple):          # (table, sorted copy or None, perm, tile masks) from build_maps
-        table, srt, perm, mask = nbr
+      if isinstance(nbr, tuple):          # (table, sorted copy or None, perm, tile masks[, halo map]) from build_maps
+        halo = nbr[4] if len(nbr) > 4 else None
+        if halo is not None and dt == torch.float16:
+          return ops.spconv_fwd_halo(x, self.tc16[key], halo, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
+                                     out_dtype=out_dtype)
+        table, srt, perm, mask = nbr[:4]
         nbr, is_sorted = (srt, True) if srt is not None else (table, False)
       Wimg = self.tc16[key] if dt == torch.float16 else self.tc[key]
       return ops.spconv_fwd(x, Wimg, nbr, n_out, in1=x2, scale=sc, shift=sh, residual=residual, relu=relu,
@@ -189,6 +195,23 @@ class ResUNetEngine:
     n = x.shape[0]
     t = self._conv(name + ".1", x, nbr, n, relu=True, out_dtype=self._want(name + ".2"))
     return self._conv(name + ".2", t, nbr, n, residual=x, relu=True, out_dtype=out_dtype)
+
+  # residual blocks convolving over the same-map 3x3x3 table of each tensor stride
+  LEVEL_BLOCKS = {1: ("block1", "block2_tr"), 2: ("block2", "block3_tr"), 4: ("block3", "block4_tr"), 8: ("block4",)}
+
+  def _halo_level(self, s) -> bool:
+    """every convolution over the stride-s same-map table runs on fp16 rows -> build the halo-staging metadata for it"""
+    return (self.use_halo and self.half and
+            all((b + sfx) in self.tc16 for b in self.LEVEL_BLOCKS[s] for sfx in (".1", ".2")))
+
+  def _bucket(self, t, keys, halo):
+    """row-bucketed form of a neighbour table for the tensor-core kernels: (table, sorted copy, perm, tile masks[, halo])"""
+    if halo:   # the halo kernel reads the original table through the permutation once, at build time: no sorted copy
+      _, perm, mask = ops.kernel_map_sort(t, keys, copy=False)
+      return (t, None, perm, mask, ops.kernel_map_halo(t, perm))
+    # copy=True: a physically re-ordered table.  Reading the original table through the permutation inside the conv
+    # (copy=False, 108 4-byte cp.async per lane per tile) was measured 1.6x slower end to end.
+    return (t,) + ops.kernel_map_sort(t, keys, copy=True)
 
   # order in which forward() first touches each table
   TABLE_ORDER = ("c1", "k3s1", "down1", "k3s2", "down2", "k3s4", "down4", "k3s8", "up4", "up2", "up1")
@@ -210,12 +233,10 @@ class ResUNetEngine:
     cms = {1: cm1, 2: cm2, 4: cm4, 8: cm8}
     sort = bool(self.tc) and self.sort_rows     # row-bucketed copies for the tensor-core kernel
 
-    def table(in_cm, out_cm, ks, transposed=False, tc=True):
+    def table(in_cm, out_cm, ks, transposed=False, tc=True, halo=False):
       if sort and tc:
         t, keys = ops.kernel_map(in_cm, out_cm, ks, transposed=transposed, with_keys=True)
-        # copy=True: a physically re-ordered table.  Reading the original table through the permutation inside the conv
-        # (copy=False, 108 4-byte cp.async per lane per tile) was measured 1.6x slower end to end.
-        return (t,) + ops.kernel_map_sort(t, keys, copy=True)
+        return self._bucket(t, keys, halo)
       return ops.kernel_map(in_cm, out_cm, ks, transposed=transposed)
 
     recipes = {}
@@ -225,7 +246,7 @@ class ResUNetEngine:
       recipes["c1"] = lambda: table(cm1, cm1, self.conv1_ks, tc=(self.conv1_ks == 3))
     for s in (1, 2, 4, 8):
       if not (s == 1 and ((self.conv1_ks == 3 and "c1" in recipes) or fused_k3s1)):
-        recipes[f"k3s{s}"] = (lambda s=s: table(cms[s], cms[s], 3))
+        recipes[f"k3s{s}"] = (lambda s=s: table(cms[s], cms[s], 3, halo=self._halo_level(s)))
     for s in (1, 2, 4):
       recipes[f"down{s}"] = (lambda s=s: table(cms[s], cms[2 * s], 3))
       recipes[f"up{s}"] = (lambda s=s: table(cms[2 * s], cms[s], 3, transposed=True))
@@ -276,7 +297,7 @@ class ResUNetEngine:
       else:   # conv1's inner probes are the stride-1 3x3x3 kernel map: emitted by the same kernel, bucketed here
         c1, (t, keys) = ops.spconv_fwd_probe(x, W, cms[1], self.conv1_ks, scale=sc, shift=sh, emit_k3=True, out_dtype=od)
         sort = bool(self.tc) and self.sort_rows
-        km.put("k3s1", ((t,) + ops.kernel_map_sort(t, keys, copy=True)) if sort else t, None)
+        km.put("k3s1", self._bucket(t, keys, self._halo_level(1)) if sort else t, None)
     else:
       c1 = self._conv("conv1", x, km["c1"] if self.conv1_ks != 1 else None, n1, out_dtype=self._want("block1.1"))
     # every layer writes the storage dtype its consumer reads (fp16 between the 64..256-channel layers, fp32 at the

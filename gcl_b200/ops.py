@@ -208,6 +208,52 @@ def kernel_map_sort(nbr: torch.Tensor, keys=None, copy: bool = True):
   return out, perm, mask
 
 
+class HaloMap:
+  """per-tile distinct-row lists + local-index tables of a bucket-sorted same-map 3x3x3 kernel map (gclb_kmap_halo_build)"""
+  __slots__ = ("slots", "tile_groups", "tile_ngroups", "counter", "status", "perm", "n_out")
+
+  def __init__(self, slots, tile_groups, tile_ngroups, counter, status, perm, n_out):
+    self.slots, self.tile_groups, self.tile_ngroups = slots, tile_groups, tile_ngroups
+    self.counter, self.status, self.perm, self.n_out = counter, status, perm, n_out
+
+
+def kernel_map_halo(nbr: torch.Tensor, perm: Optional[torch.Tensor]) -> HaloMap:
+  """Halo staging metadata for the tcgen05 halo kernel.  nbr is the ORIGINAL table [n_out, 27]; perm the bucket order from
+  kernel_map_sort (tile row t = output row perm[t]).  The record buffer is sized for the worst case (22 KB per tile; a
+  LiDAR map touches ~1/6 of it), so there is no overflow path and no host synchronisation."""
+  n_out, K = nbr.shape
+  assert K == 27
+  lib = _lib.load()
+  dev = nbr.device
+  tiles = (n_out + 127) // 128
+  nbytes, maxg = int(lib.gclb_kmap_halo_bytes(n_out)), int(lib.gclb_kmap_halo_max_groups())
+  slots = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+  tile_groups = torch.empty((max(tiles, 1), maxg, 2), dtype=torch.int32, device=dev)
+  tile_ngroups = torch.empty(max(tiles, 1), dtype=torch.int32, device=dev)
+  cs = torch.zeros(2, dtype=torch.int64, device=dev)          # [0] granules used, [1] status (low word)
+  call("gclb_kmap_halo_build", ptr(nbr), n_out, ptr(perm), ptr(slots), nbytes, ptr(tile_groups), ptr(tile_ngroups),
+       cs.data_ptr(), cs.data_ptr() + 8, stream())
+  return HaloMap(slots, tile_groups, tile_ngroups, cs[0:1], cs[1:2], perm, n_out)
+
+
+def spconv_fwd_halo(in0: torch.Tensor, Wimg: torch.Tensor, halo: HaloMap, in1: Optional[torch.Tensor] = None, scale=None,
+                    shift=None, residual=None, relu=False, normalize: bool = False, out_dtype=None) -> torch.Tensor:
+  """same-map 3x3x3 convolution on fp16 activations through the halo-staging tcgen05 kernel; Wimg from
+  weights_to_tc(W, half=True)."""
+  require_cuda(in0, Wimg, in1, scale, shift, residual)
+  assert in0.dtype == torch.float16 and Wimg.dtype == torch.float16
+  K, cout, cin = Wimg.shape
+  c0, c1 = in0.shape[1], (in1.shape[1] if in1 is not None else 0)
+  assert K == 27 and c0 + c1 == cin
+  out = torch.empty((halo.n_out, cout), dtype=out_dtype or in0.dtype, device=in0.device)
+  flags = int(bool(relu)) | (2 if normalize else 0) | 8 | (16 if out.dtype == torch.float16 else 0)
+  flags |= 32 if f16_slab(c0, c1) == 32 else 0
+  call("gclb_spconv_fwd_halo", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(Wimg), cout, ptr(halo.slots),
+       ptr(halo.tile_groups), ptr(halo.tile_ngroups), ptr(halo.perm), ptr(scale), ptr(shift), ptr(residual), flags, ptr(out),
+       halo.n_out, stream())
+  return out
+
+
 def spconv_fwd(in0: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                in1: Optional[torch.Tensor] = None, scale=None, shift=None, residual=None, relu=False,
                out: Optional[torch.Tensor] = None, algo: int = 0, normalize: bool = False,

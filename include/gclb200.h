@@ -202,6 +202,35 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
                           int64_t capacity, const int32_t* coords4, int64_t n, int32_t tensor_stride, int32_t dilation,
                           const float* scale, const float* shift, const float* residual, int32_t relu_flags, void* out,
                           int32_t* nbr3_out, uint8_t* row_keys, uint32_t* row_masks, int32_t* key_hist, void* stream);
+/* ------------------------------------------------------------------------------------------------------
+ * K3 with operand reuse inside the SM ("halo staging") for SAME-MAP 3x3x3 convolutions on fp16 activations
+ * (model/residual_block.py:23-33,40-53: the two convolutions of every residual block; 16 of the 22 conv launches of
+ * ResUNetBN2C.forward, model/resunet.py:173-232).  Neighbouring output rows share most input rows; the direct-gather kernel
+ * above fetches every input row ~7x from L2.  Here a precomputed list names the DISTINCT input rows of each 128-row tile
+ * (split into groups of <= 384 rows), they are staged in shared memory once per channel slab by TMA gather, and the per-offset
+ * tensor-core operand is assembled from the staged rows.  Same arithmetic, same results (bit-identical to algo 2 with the
+ * same row order), 3-4x fewer bytes through the L2->SM fabric.
+ *
+ * gclb_kmap_halo_build: nbr int32 [n_out, 27] (ORIGINAL order), row_perm int32 [n_out] from gclb_kmap_sort_rows (or NULL);
+ *   records: caller buffer of record_bytes >= gclb_kmap_halo_bytes(n_out) bytes (the worst case, so the build cannot run out
+ *   of space; typical use is ~1/6 of it), 16-byte aligned: packed variable-size group records
+ *   { header 64 B | int32 distinct rows | uint16 local index [offsets of the group][128] };
+ *   tile_groups int32 [ceil(n_out/128), gclb_kmap_halo_max_groups(), 2] = (offset, size) of every record in 16-byte granules;
+ *   tile_ngroups int32 [ceil(n_out/128)]; counter uint64[1] caller-zeroed (granules used); status: GCLB_ST_FULL if the buffer
+ *   was smaller than the worst case and did not suffice (the map must then not be used; the kernel traps on such a record).
+ * gclb_spconv_fwd_halo: arguments as gclb_spconv_fwd (K = 27; flags bit 3 required; bits 0, 1, 4, 5 as there); W is the
+ *   fp16 image from gclb_weights_to_tc_f16 with the matching slab width. */
+size_t gclb_kmap_halo_bytes(int64_t n_out);
+/* bring-up helper: per-CTA cycle accounting of the last gclb_spconv_fwd_halo launch run with GCLB_HALO_DBG bit 9 (host uint64 [148][16]) */
+int gclb_debug_halo_prof(unsigned long long* out_host);
+int32_t gclb_kmap_halo_max_groups(void);
+int gclb_kmap_halo_build(const int32_t* nbr, int64_t n_out, const int32_t* row_perm, void* records, size_t record_bytes,
+                         int32_t* tile_groups, int32_t* tile_ngroups, uint64_t* counter, int32_t* status, void* stream);
+int gclb_spconv_fwd_halo(const void* in0, int32_t c0, const void* in1, int32_t c1, int64_t n_in, const void* W, int32_t cout,
+                         const void* records, const int32_t* tile_groups, const int32_t* tile_ngroups, const int32_t* row_perm,
+                         const float* scale, const float* shift, const void* residual, int32_t flags, void* out,
+                         int64_t n_out, void* stream);
+
 /* wgrad: gW[k, c, :] = sum over pairs in[nbr[o,k], c] * gout[o, :]   (a18; lib/colocation_trainer.py:879) */
 int gclb_spconv_wgrad(const float* in, int32_t cin, int64_t n_in, const float* gout, int32_t cout, int64_t n_out,
                       const int32_t* nbr, int32_t K, float* gW, void* stream);
