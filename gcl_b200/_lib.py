@@ -34,6 +34,7 @@ SIGNATURES = {
                                   _i32, _p]),
     "gclb_kmap_halo_bytes": (_sz, [_i64]),
     "gclb_debug_halo_prof": (C.c_int, [_p]),
+    "gclb_debug_umma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p, _p]),
     "gclb_kmap_halo_max_groups": (_i32, []),
     "gclb_kmap_halo_build": (C.c_int, [_p, _i64, _p, _p, _sz, _p, _p, _p, _p, _p]),
     "gclb_spconv_fwd_halo": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "gclb_nn": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "gclb_subsample": (C.c_int, [_p, _p, _i64, _i32, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),
     "gclb_mutual_filter": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p]),
+    "gclb_sc2pcr_workspace_bytes": (_sz, [_i64, _i32, C.c_double]),
+    "gclb_sc2pcr": (C.c_int, [_p, _p, _p, _i32, _i64, _f32, _f32, _f32, C.c_double, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "gclb_loss_workspace_bytes": (_sz, [_i64, _i64]),
     "gclb_debug_tma_gather4": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "gclb_group_loss": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _f32, _f32, _f32,

@@ -365,11 +365,13 @@ __global__ void __launch_bounds__(kHThreads, 1) spconv_fwd_halo_kernel(ConvParam
             tc_fence_after();
             const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
             const uint32_t b_s = a_s + A_BYTES;
-            if (!(dbg & 32))
+            if (!(dbg & 32)) {
+              constexpr uint32_t HI = MODE == 2 ? kDescHiSw64 : kDescHiSw128;
+              const uint32_t a_lo = desc_lo(a_s), b_lo = desc_lo(b_s);
+              if (issued == 0) umma_f16_lo<HI, false>(d_tmem, a_lo, b_lo, idesc);
+              else umma_f16_lo<HI, true>(d_tmem, a_lo, b_lo, idesc);
 #pragma unroll
-            for (int ks = 0; ks < ROWB / 32; ++ks) {
-              if (MODE == 2) umma_f16(d_tmem, make_desc_sw64(a_s + ks * 32), make_desc_sw64(b_s + ks * 32), idesc, (issued | ks) ? 1u : 0u);
-              else umma_f16(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (issued | ks) ? 1u : 0u);
+              for (int ks = 1; ks < ROWB / 32; ++ks) umma_f16_lo<HI, true>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc);
             }
             umma_commit(&sh.empty[stage]);
           }

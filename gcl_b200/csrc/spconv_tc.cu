@@ -165,11 +165,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams
           tc_fence_after();
           const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
           const uint32_t b_s = a_s + A_BYTES;
+          if constexpr (HALF) {   // lean issue path (tc_common.cuh): the issuing thread, not the tensor pipe, bounds N <= 128
+            constexpr uint32_t HI = MODE == 2 ? kDescHiSw64 : kDescHiSw128;
+            const uint32_t a_lo = desc_lo(a_s), b_lo = desc_lo(b_s);
+            if (i == 0) umma_f16_lo<HI, false>(d_tmem, a_lo, b_lo, idesc);
+            else umma_f16_lo<HI, true>(d_tmem, a_lo, b_lo, idesc);
 #pragma unroll
-          for (int ks = 0; ks < ROWB / 32; ++ks) {   // MMAs of 32 bytes of K (8 tf32 / 16 fp16) inside the swizzle row
-            if (MODE == 2) umma_f16(d_tmem, make_desc_sw64(a_s + ks * 32), make_desc_sw64(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
-            else if (MODE == 1) umma_f16(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
-            else umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+            for (int ks = 1; ks < ROWB / 32; ++ks) umma_f16_lo<HI, true>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < ROWB / 32; ++ks)   // MMAs of 32 bytes of K (8 tf32) inside the swizzle row
+              umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
           }
           umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
         }

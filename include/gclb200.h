@@ -223,6 +223,8 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
 size_t gclb_kmap_halo_bytes(int64_t n_out);
 /* bring-up helper: per-CTA cycle accounting of the last gclb_spconv_fwd_halo launch run with GCLB_HALO_DBG bit 9 (host uint64 [148][16]) */
 int gclb_debug_halo_prof(unsigned long long* out_host);
+/* bring-up helper: tcgen05.mma issue / completion cycles (M = 128, N = n, K = 16, kind::f16), out_dev int64[2] */
+int gclb_debug_umma_rate(int32_t n, int32_t n_mma, int32_t per_commit, int32_t n_acc, int32_t elect, long long* out_dev, void* stream);
 int32_t gclb_kmap_halo_max_groups(void);
 int gclb_kmap_halo_build(const int32_t* nbr, int64_t n_out, const int32_t* row_perm, void* records, size_t record_bytes,
                          int32_t* tile_groups, int32_t* tile_ngroups, uint64_t* counter, int32_t* status, void* stream);
@@ -327,6 +329,26 @@ int gclb_group_loss_bwd(const float* F, int64_t N, int32_t C, const int64_t* gro
  * fp32 matrix X [n, c] into a SWIZZLE_128B shared-memory tile, dumped to out256 (device, 256 floats). */
 int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_rows, int32_t col, const int32_t* rows4_host,
                            float* out256, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * SC2-PCR registration from putative correspondences, batched over independent problems (scan pairs).
+ * Replaces Matcher.SC2_PCR, /root/reference/scripts/SC2_PCR/SC2_PCR.py:304-381 (with pick_seeds :34-58, cal_seed_trans
+ * :60-168, cal_leading_eigenvector :170-196, post_refinement :235-274 and common.py:7-45 rigid_transform_3d), called right
+ * after feature matching at scripts/test_kitti.py:180-182.
+ *   src_xyz, tgt_xyz float32 [sum n_p, 3]: row i of src corresponds to row i of tgt; ptr int64 [n_problems+1] (device)
+ *   n_max: host upper bound of the segment lengths; only the first max_points (<= 8192) rows of a segment are used (:321-324)
+ *   d_thre, inlier_threshold, nms_radius, ratio, num_iterations, k1, k2 (<= 32): config_json/config_KITTI.json;
+ *   refine_iters: 20 in the reference (:378); the refinement threshold is 0.10 when inlier_threshold == 0.10 else 1.2 (:249-252)
+ *   trans_out float32 [n_problems, 4, 4] (src -> tgt); info_out int32 [n_problems, 4] = rows used, seeds, inliers of the best
+ *   seed hypothesis, inliers of the last refinement iteration (a problem without seeds gets the identity and seeds = 0)
+ *   workspace: gclb_sc2pcr_workspace_bytes(n_max, n_problems, ratio)
+ * Equal scores resolve to the smaller index (torch.argsort leaves ties unspecified); rotations come from Horn's quaternion
+ * form of the weighted Kabsch problem (same optimum as the SVD with the det correction). */
+size_t gclb_sc2pcr_workspace_bytes(int64_t n_max, int32_t n_problems, double ratio);
+int gclb_sc2pcr(const float* src_xyz, const float* tgt_xyz, const int64_t* ptr, int32_t n_problems, int64_t n_max,
+                float d_thre, float inlier_threshold, float nms_radius, double ratio, int32_t num_iterations, int32_t k1,
+                int32_t k2, int32_t max_points, int32_t refine_iters, float* trans_out, int32_t* info_out, void* workspace,
+                void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Positive-group construction of the GCL colocation loaders:

@@ -1,0 +1,84 @@
+"""SC2-PCR registration on the GPU (gcl_b200/csrc/sc2pcr.cu) against (1) transforms produced by the reference's
+own Matcher.SC2_PCR (tests/golden/sc2pcr.npz) and (2) the CPU oracle restatement on further seeds.  Floating-point path:
+transforms agree to 1e-4 (rotation entries and translations in metres) -- the test states the bar next to each assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import sc2pcr_correspondences
+from oracle import sc2pcr as osc
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sc2pcr.npz")
+KITTI = dict(inlier_threshold=0.6, num_node=8000, use_mutual=False, d_thre=0.1, num_iterations=20, ratio=0.2, nms_radius=0.6,
+             max_points=8000, k1=30, k2=20)          # scripts/SC2_PCR/config_json/config_KITTI.json
+TOL = 1e-4
+
+
+def _matcher():
+  from gcl_b200.registration import Matcher
+  return Matcher(**KITTI)
+
+
+def test_sc2pcr_reproduces_reference_golden_transforms():
+  g = np.load(GOLD)
+  m = _matcher()
+  for c in range(3):
+    src, tgt = torch.from_numpy(g[f"c{c}_src"])[None].to(DEV), torch.from_numpy(g[f"c{c}_tgt"])[None].to(DEV)
+    T = m.SC2_PCR(src, tgt)
+    assert T.shape == (1, 4, 4)
+    err = np.abs(T[0].cpu().numpy() - g[f"c{c}_trans"]).max()
+    print(f"case {c}: |T - T_reference|max = {err:.2e}")
+    assert err < TOL, (c, err)
+
+
+@pytest.mark.parametrize("seed,n,ratio", [(11, 2000, 0.25), (12, 5000, 0.1), (13, 700, 0.5), (14, 5000, 0.35)])
+def test_sc2pcr_vs_oracle_more_seeds(seed, n, ratio):
+  src, tgt, T_gt = sc2pcr_correspondences(seed, n, ratio)
+  want = osc.sc2_pcr(torch.from_numpy(src)[None], torch.from_numpy(tgt)[None], osc.SC2Config())[0].numpy()
+  got = _matcher().SC2_PCR(torch.from_numpy(src)[None].to(DEV), torch.from_numpy(tgt)[None].to(DEV))[0].cpu().numpy()
+  err = np.abs(got - want).max()
+  print(f"seed {seed} n={n}: |T - T_oracle|max = {err:.2e}; |T - T_gt|max = {np.abs(got - T_gt).max():.3f}")
+  assert err < TOL, err
+  assert np.abs(got - T_gt).max() < 0.05               # and it is the right answer
+
+
+def test_sc2pcr_batched_equals_single_and_truncates():
+  from gcl_b200.registration import sc2_pcr_batch
+  cases = [sc2pcr_correspondences(s, n, r) for s, n, r in [(21, 900, 0.3), (22, 1500, 0.2), (23, 300, 0.6)]]
+  src = torch.from_numpy(np.concatenate([c[0] for c in cases])).to(DEV)
+  tgt = torch.from_numpy(np.concatenate([c[1] for c in cases])).to(DEV)
+  lens = [len(c[0]) for c in cases]
+  seg = torch.tensor(np.cumsum([0] + lens), dtype=torch.int64, device=DEV)
+  kw = dict(d_thre=0.1, inlier_threshold=0.6, nms_radius=0.6, ratio=0.2, num_iterations=20, k1=30, k2=20)
+  Tb, info = sc2_pcr_batch(src, tgt, seg, max(lens), **kw)
+  assert info[:, 0].tolist() == lens and info[:, 1].tolist() == [int(n * 0.2) for n in lens]
+  m = _matcher()
+  for i, c in enumerate(cases):
+    Ti = m.SC2_PCR(torch.from_numpy(c[0])[None].to(DEV), torch.from_numpy(c[1])[None].to(DEV))[0]
+    assert torch.equal(Ti, Tb[i])                        # batching changes nothing, bit for bit
+    assert np.abs(Tb[i].cpu().numpy() - c[2]).max() < 0.05
+  # max_points: only the first rows are used (SC2_PCR.py:321-324)
+  Tt, info_t = sc2_pcr_batch(src[:900], tgt[:900], seg[:2], 900, max_points=500, **kw)
+  T5 = m.SC2_PCR(src[None, :500], tgt[None, :500])[0]
+  assert int(info_t[0, 0]) == 500 and torch.equal(Tt[0], T5)
+  # determinism
+  Tb2, _ = sc2_pcr_batch(src, tgt, seg, max(lens), **kw)
+  assert torch.equal(Tb, Tb2)
+
+
+def test_estimator_api_matches_reference_conventions():
+  """Matcher.estimator (SC2_PCR.py:383-411): match_pair on unit descriptors, SC2-PCR, inlier labels"""
+  rng = np.random.RandomState(5)
+  src, tgt, T_gt = sc2pcr_correspondences(31, 1500, 1.0, noise=0.02)       # all rows are true correspondences ...
+  F = torch.nn.functional.normalize(torch.from_numpy(rng.randn(1500, 32).astype(np.float32)), dim=1)
+  perm = rng.permutation(1500)                                               # ... hidden behind a permutation of the target
+  F1 = F[perm] + 0.01 * torch.from_numpy(rng.randn(1500, 32).astype(np.float32))
+  F1 = torch.nn.functional.normalize(F1, dim=1)
+  T, labels, sc, tc = _matcher().estimator(torch.from_numpy(src)[None].to(DEV), torch.from_numpy(tgt[perm])[None].to(DEV),
+                                           F[None].to(DEV), F1[None].to(DEV))
+  assert T.shape == (1, 4, 4) and labels.shape == (1, 1500) and sc.shape == tc.shape == (1, 1500, 3)
+  assert np.abs(T[0].cpu().numpy() - T_gt).max() < 0.02 and labels.mean().item() > 0.95
