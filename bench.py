@@ -393,6 +393,22 @@ def main():
   ms_e2e, _ = timed_region(step_e2e, args.steps, pinned)
   new_segments_e2e = n_segments() - seg1
 
+  # registered pairs/s: the same path + SC2-PCR registration of every pair (scripts/test_kitti.py:180-182), transforms read back
+  matcher.do_register = True
+
+  def step_registered(s, out=None):
+    if out is None:
+      x, p = resident[s % n_batches]
+      out = matcher.match(x, p)
+    out["trans"].cpu()
+    matcher.check(out)
+    return out["n_voxels_total"]
+
+  settle(step_registered, resident, max_rounds=4)
+  reg_steps = max(5, args.steps // 2)
+  ms_reg, _ = timed_region(step_registered, reg_steps, resident)
+  matcher.do_register = False
+
   total_pairs = args.pairs * args.steps * world
   value = total_pairs / (ms * 1e-3)
   e2e_value = total_pairs / (ms_e2e * 1e-3)
@@ -414,6 +430,10 @@ def main():
                                    if (lib.gclb_has_tcgen05() and args.algo != 1) else "fp32 CUDA-core implicit GEMM")},
           "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(ms_e2e / args.steps, 3)},
+          "registered": {"metric": "registered_scan_pairs_per_sec", "value": round(args.pairs * reg_steps * world / (ms_reg * 1e-3), 2),
+                         "unit": "pairs/s", "ms_per_step": round(ms_reg / reg_steps, 3), "steps": reg_steps,
+                         "what": "same step + SC2-PCR registration of every pair on the GPU (5000 putative correspondences per pair, "
+                                 "config_KITTI.json), 4x4 transforms read back"},
           "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": [int(new_segments), int(new_segments_e2e)], "clocks": clk, "roofline": roof}
   if world == 1 and not args.no_cpu_baseline:
     r = run_cpu(steps=5, warmup=1, n_pairs_per_step=1)

@@ -530,6 +530,24 @@ __global__ void __launch_bounds__(1024) sc_refine_kernel(ScParams p) {
   if (threadIdx.x == 0) info[3] = last_cnt;
 }
 
+// putative correspondences of a batch of matched scan pairs as point coordinates (what Matcher.match_pair returns,
+// SC2_PCR.py:297-302): row i of segment p pairs sample i of scan 0 with its feature-space nearest neighbour in scan 1
+__global__ void __launch_bounds__(256) corr_points_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ umap,
+                                                          const int64_t* __restrict__ sel0, const int64_t* __restrict__ sel1,
+                                                          const int64_t* __restrict__ a_ptr, const int64_t* __restrict__ b_ptr,
+                                                          const int64_t* __restrict__ idx01, int n_pairs,
+                                                          float* __restrict__ src, float* __restrict__ tgt) {
+  const int64_t n_total = a_ptr[n_pairs];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_pairs;                    // segment of row i: a_ptr[lo] <= i < a_ptr[lo + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a_ptr[mid] <= i) lo = mid; else hi = mid; }
+    const int64_t v0 = sel0[i], v1 = sel1[b_ptr[lo] + idx01[i]];
+    const int64_t p0 = umap ? umap[v0] : v0, p1 = umap ? umap[v1] : v1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { src[i * 3 + c] = xyz[p0 * 3 + c]; tgt[i * 3 + c] = xyz[p1 * 3 + c]; }
+  }
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t sc_layout(ScParams& p, unsigned char* base) {
@@ -554,6 +572,20 @@ static size_t sc_layout(ScParams& p, unsigned char* base) {
 using namespace gclb;
 
 extern "C" {
+
+int gclb_corr_points(const float* xyz, const int64_t* unique_map, const int64_t* sel0, const int64_t* sel1,
+                     const int64_t* a_ptr, const int64_t* b_ptr, const int64_t* idx01, int32_t n_pairs, int64_t n_total_bound,
+                     float* src_out, float* tgt_out, void* stream) {
+  GCLB_CHECK_ARG(xyz && sel0 && sel1 && a_ptr && b_ptr && idx01 && src_out && tgt_out && n_pairs >= 1, "bad arguments");
+  if (n_total_bound <= 0) return GCLB_OK;
+  int64_t blocks = (n_total_bound + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  corr_points_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xyz, unique_map, sel0, sel1, a_ptr, b_ptr, idx01, n_pairs,
+                                                                        src_out, tgt_out);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
 
 size_t gclb_sc2pcr_workspace_bytes(int64_t n_max, int32_t n_problems, double ratio) {
   if (n_max < 1 || n_problems < 1) return 0;

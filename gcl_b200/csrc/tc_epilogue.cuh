@@ -9,7 +9,9 @@ namespace gclb {
 
 // acc_full / acc_empty: the accumulator's mbarriers; acc_n_act: #populated offsets of the tile it holds (0 => zeros);
 // tmem_acc: TMEM address of the accumulator (lane 0, first column); amax_bits: running fp16-range monitor (common.cuh)
-template <int COUT, bool HALF>
+// DUAL: two MMA issuers accumulated alternate pipeline stages into two accumulators (tmem_acc and tmem_acc + COUT; acc_n_act
+// is int[2]: stages each one issued, 0 => that accumulator holds stale data); the epilogue adds them in a fixed order.
+template <int COUT, bool HALF, bool DUAL = false>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, int quarter, int lane, int normalize,
                                                  uint64_t* acc_full, uint32_t acc_parity, uint64_t* acc_empty,
                                                  const int* acc_n_act, uint32_t tmem_acc, uint32_t& amax_bits, int dbg = 0) {
@@ -31,12 +33,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, 
   for (int q = 0; q < RV; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
-  const bool empty_tile = (*reinterpret_cast<const volatile int*>(acc_n_act) == 0);
+  const bool has0 = *reinterpret_cast<const volatile int*>(acc_n_act) != 0;
+  const bool has1 = DUAL && *reinterpret_cast<const volatile int*>(acc_n_act + 1) != 0;
+  const bool empty_tile = !has0 && !has1;
   const uint32_t t_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
   for (int n0 = 0; n0 < COUT; n0 += 32) {
     uint32_t v[32];
     tmem_ld32(t_addr + (uint32_t)n0, v);
+    if constexpr (DUAL) {
+      uint32_t v2[32];
+      tmem_ld32(t_addr + (uint32_t)(COUT + n0), v2);
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        v[q] = __float_as_uint((has0 ? __uint_as_float(v[q]) : 0.f) + (has1 ? __uint_as_float(v2[q]) : 0.f));
+    }
     float4 rn[RV];                                      // residual of the NEXT 32 columns, in flight during this chunk
     const bool more = (n0 + 32 < COUT);
 #pragma unroll

@@ -13,12 +13,14 @@ from .engine import ResUNetEngine
 
 
 class PairMatcher:
-  def __init__(self, model, voxel: float = 0.3, subsample: int = 5000, device="cuda", seed: int = 0, algo: int = 0):
+  def __init__(self, model, voxel: float = 0.3, subsample: int = 5000, device="cuda", seed: int = 0, algo: int = 0,
+               register: bool = False):
     self.engine = model if isinstance(model, ResUNetEngine) else ResUNetEngine(model, device=device, algo=algo)
     self.voxel, self.subsample = float(voxel), int(subsample)
     self.device = torch.device(device)
     self.seed, self.calls = int(seed) * 1000003, 0
     self._streams = None
+    self.do_register = bool(register)    # match() also runs SC2-PCR on every pair: out["trans"], out["reg_info"]
 
   @torch.no_grad()
   def match(self, xyz: torch.Tensor, cloud_ptr: torch.Tensor):
@@ -40,9 +42,35 @@ class PairMatcher:
     idx01, d01, idx10, d10, a_dev, b_dev, ws = ops.nn_search(feats, feats, sel_ptr[0], sel_ptr[1], both=True,
                                                              a_rows=sel[0], b_rows=sel[1], max_n=cap, max_m=cap)
     pairs, pair_ptr = ops.mutual_filter(idx01, idx10, a_dev, b_dev, ws)
-    return dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel[0], sel1=sel[1], a_ptr=a_dev, b_ptr=b_dev, idx01=idx01,
-                idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords,
-                status=self.engine.range_status)
+    out = dict(pairs=pairs, pair_ptr=pair_ptr, sel0=sel[0], sel1=sel[1], a_ptr=a_dev, b_ptr=b_dev, idx01=idx01,
+               idx10=idx10, unique_map=umap, cloud_rows=cloud_rows, n_voxels_total=cm.n, feats=feats, coords=cm.coords,
+               status=self.engine.range_status)
+    if self.do_register:
+      out["trans"], out["reg_info"] = self.register(xyz, out)
+    return out
+
+  # scripts/SC2_PCR/config_json/config_KITTI.json
+  SC2_KITTI = dict(d_thre=0.1, inlier_threshold=0.6, nms_radius=0.6, ratio=0.2, num_iterations=20, k1=30, k2=20, max_points=8000)
+
+  @torch.no_grad()
+  def register(self, xyz: torch.Tensor, out: dict, **sc2_cfg):
+    """SC2-PCR registration of every pair of a matched batch (scripts/test_kitti.py:180-182: `matcher.estimator(...)` right
+    after the features): the putative correspondences are sample i of scan 0 <-> its feature-space nearest neighbour among the
+    samples of scan 1 (Matcher.match_pair), as point coordinates of `xyz` (the tensor given to match()).
+    Returns (trans float32 [n_pairs, 4, 4] scan 0 -> scan 1, info int32 [n_pairs, 4]); everything stays on the device."""
+    from . import registration
+    cfg = dict(self.SC2_KITTI, **sc2_cfg)
+    a_ptr, b_ptr = out["a_ptr"], out["b_ptr"]
+    n_pairs = a_ptr.numel() - 1
+    cap = self.subsample if self.subsample > 0 else int(out["n_voxels_total"])
+    bound = n_pairs * cap
+    dev = out["idx01"].device
+    xyz = xyz if xyz.is_cuda else xyz.to(dev, non_blocking=True)
+    src = torch.empty((bound, 3), dtype=torch.float32, device=dev)
+    tgt = torch.empty((bound, 3), dtype=torch.float32, device=dev)
+    _lib.call("gclb_corr_points", _lib.ptr(xyz.contiguous()), _lib.ptr(out["unique_map"]), _lib.ptr(out["sel0"]), _lib.ptr(out["sel1"]),
+              _lib.ptr(a_ptr), _lib.ptr(b_ptr), _lib.ptr(out["idx01"]), n_pairs, bound, _lib.ptr(src), _lib.ptr(tgt), _lib.stream())
+    return registration.sc2_pcr_batch(src, tgt, a_ptr, cap, **cfg)
 
   @staticmethod
   def check(out):

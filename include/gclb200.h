@@ -345,6 +345,13 @@ int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_row
  * Equal scores resolve to the smaller index (torch.argsort leaves ties unspecified); rotations come from Horn's quaternion
  * form of the weighted Kabsch problem (same optimum as the SVD with the det correction). */
 size_t gclb_sc2pcr_workspace_bytes(int64_t n_max, int32_t n_problems, double ratio);
+/* the putative correspondences of a matched batch as coordinates (Matcher.match_pair's return, SC2_PCR.py:297-302), straight
+ * from the outputs of gclb_subsample / gclb_nn: row i of segment p = (xyz[unique_map[sel0[i]]], xyz[unique_map[sel1[b_ptr[p] +
+ * idx01[i]]]]); unique_map may be NULL (sel* then index xyz directly); n_total_bound >= a_ptr[n_pairs] sizes the grid;
+ * src_out / tgt_out float32 [n_total_bound, 3] */
+int gclb_corr_points(const float* xyz, const int64_t* unique_map, const int64_t* sel0, const int64_t* sel1,
+                     const int64_t* a_ptr, const int64_t* b_ptr, const int64_t* idx01, int32_t n_pairs, int64_t n_total_bound,
+                     float* src_out, float* tgt_out, void* stream);
 int gclb_sc2pcr(const float* src_xyz, const float* tgt_xyz, const int64_t* ptr, int32_t n_problems, int64_t n_max,
                 float d_thre, float inlier_threshold, float nms_radius, double ratio, int32_t num_iterations, int32_t k1,
                 int32_t k2, int32_t max_points, int32_t refine_iters, float* trans_out, int32_t* info_out, void* workspace,

@@ -78,7 +78,49 @@ def test_estimator_api_matches_reference_conventions():
   perm = rng.permutation(1500)                                               # ... hidden behind a permutation of the target
   F1 = F[perm] + 0.01 * torch.from_numpy(rng.randn(1500, 32).astype(np.float32))
   F1 = torch.nn.functional.normalize(F1, dim=1)
-  T, labels, sc, tc = _matcher().estimator(torch.from_numpy(src)[None].to(DEV), torch.from_numpy(tgt[perm])[None].to(DEV),
-                                           F[None].to(DEV), F1[None].to(DEV))
+  from gcl_b200.registration import Matcher
+  m = Matcher(**dict(KITTI, num_node="all"))
+  T, labels, sc, tc = m.estimator(torch.from_numpy(src)[None].to(DEV), torch.from_numpy(tgt[perm])[None].to(DEV),
+                                  F[None].to(DEV), F1[None].to(DEV))
   assert T.shape == (1, 4, 4) and labels.shape == (1, 1500) and sc.shape == tc.shape == (1, 1500, 3)
   assert np.abs(T[0].cpu().numpy() - T_gt).max() < 0.02 and labels.mean().item() > 0.95
+  # config_KITTI.json's num_node = 8000: the reference draws 8000 nodes WITH replacement (SC2_PCR.py:282-284), also from 1500
+  np.random.seed(0)
+  T2, labels2, sc2, _ = _matcher().estimator(torch.from_numpy(src)[None].to(DEV), torch.from_numpy(tgt[perm])[None].to(DEV),
+                                             F[None].to(DEV), F1[None].to(DEV))
+  assert labels2.shape == (1, 8000) and sc2.shape == (1, 8000, 3) and np.abs(T2[0].cpu().numpy() - T_gt).max() < 0.02
+
+
+def test_pair_matcher_register_recovers_the_relative_pose():
+  """end to end on synthetic LoKITTI-style pairs: features -> NN -> correspondences -> SC2-PCR, everything on the device; the
+  batched result equals registering each pair's correspondences through Matcher.SC2_PCR.  (The network has seeded RANDOM
+  weights -- no checkpoint offline -- so the pose error against the generator's ground truth is reported, not asserted.)"""
+  import bench
+  from gcl_b200 import MinkowskiEngine as ME, synth
+  from gcl_b200.pipeline import PairMatcher
+  matcher = PairMatcher(bench.seeded_model(ME), voxel=0.3, subsample=5000, device=DEV, seed=1)
+  clouds, Ts = [], []
+  for s in range(2):
+    x0, x1, T01 = synth.scan_pair(scene_seed=50 + s, pair_seed=60 + s, max_d=12.0)
+    clouds += [x0, x1]; Ts.append(T01)
+  xyz = torch.from_numpy(np.concatenate(clouds)).to(DEV)
+  ptr = torch.tensor(np.cumsum([0] + [len(c) for c in clouds]))
+  out = matcher.match(xyz, ptr)
+  trans, info = matcher.register(xyz, out)
+  assert trans.shape == (2, 4, 4) and info.shape == (2, 4) and info[:, 0].tolist() == [5000, 5000]
+  assert bool(torch.isfinite(trans).all())
+  for p_ in range(2):
+    R, t = trans[p_, :3, :3].cpu().double().numpy(), trans[p_, :3, 3].cpu().double().numpy()
+    assert abs(np.linalg.det(R) - 1) < 1e-4 and np.abs(R @ R.T - np.eye(3)).max() < 1e-4       # a proper rotation
+    rte = np.linalg.norm(t - Ts[p_][:3, 3])
+    rre = np.degrees(np.arccos(np.clip((np.trace(R.T @ Ts[p_][:3, :3]) - 1) / 2, -1, 1)))
+    print(f"pair {p_}: inliers {info[p_, 2].item()} -> {info[p_, 3].item()}  RTE {rte:.2f} m  RRE {rre:.2f} deg (random weights)")
+  # same correspondences through the single-problem API
+  a_ptr, b_ptr = out["a_ptr"].tolist(), out["b_ptr"].tolist()
+  um = out["unique_map"]
+  for p_ in range(2):
+    s0 = out["sel0"][a_ptr[p_]:a_ptr[p_ + 1]]
+    j = out["idx01"][a_ptr[p_]:a_ptr[p_ + 1]] + b_ptr[p_]
+    src, tgt = xyz[um[s0]], xyz[um[out["sel1"][j]]]
+    T1 = _matcher().SC2_PCR(src[None], tgt[None])[0]
+    assert torch.equal(T1, trans[p_])
