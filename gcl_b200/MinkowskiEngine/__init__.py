@@ -389,8 +389,9 @@ class MinkowskiConvolutionTranspose(_ConvBase):
 
 class MinkowskiBatchNorm(nn.Module):
   """BatchNorm1d over the rows of .F; child module `bn` keeps the checkpoint keys (A8, A10).
-  Eval mode without autograd runs libgclb200's fused affine kernel; training mode keeps torch's BatchNorm1d
-  so that autograd and running statistics follow the reference exactly."""
+  Eval mode without autograd runs libgclb200's fused affine kernel; training mode runs libgclb200's own statistics /
+  normalise / backward kernels (csrc/bn.cu) with BatchNorm1d's semantics: biased batch variance for the normalisation,
+  unbiased for running_var, momentum update, num_batches_tracked."""
 
   def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
     super().__init__()
@@ -408,13 +409,67 @@ class MinkowskiBatchNorm(nn.Module):
       shift = shift + bn.bias.detach()
     return scale.contiguous(), shift.contiguous()
 
-  def forward(self, x: SparseTensor) -> SparseTensor:
+  def forward(self, x: SparseTensor, relu: bool = False) -> SparseTensor:
+    """relu=True fuses the MEF.relu that follows the norm in every residual block (gcl_b200 extension; the reference's
+    model files call MEF.relu separately and get the same numbers through two launches)."""
     bn = self.bn
-    use_kernel = (not bn.training) and bn.track_running_stats and not (torch.is_grad_enabled() and x.F.requires_grad)
-    if use_kernel:
-      scale, shift = self.folded()
-      return x._like(ops.affine_act(x.F.detach(), scale, shift))
-    return x._like(bn(x.F))
+    f = x.F
+    batch_stats = bn.training or not bn.track_running_stats
+    if not batch_stats:
+      if not (torch.is_grad_enabled() and f.requires_grad):
+        scale, shift = self.folded()
+        return x._like(ops.affine_act(f.detach(), scale, shift, relu=relu))
+      out = bn(f)                       # eval-mode BN inside an autograd graph (fine-tuning with frozen statistics): ATen
+      return x._like(torch.relu(out) if relu else out)
+    if f.shape[1] % 4 != 0 or f.dtype != torch.float32 or f.shape[0] < 1:
+      out = bn(f)
+      return x._like(torch.relu(out) if relu else out)
+    # training mode: libgclb200's fused statistics / normalise(+ReLU) kernels with their own backward
+    factor = 0.0
+    if bn.track_running_stats:
+      bn.num_batches_tracked += 1
+      factor = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else float(bn.momentum)
+    out = _BatchNormTrainFn.apply(f, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                                  bn.running_var if bn.track_running_stats else None, float(bn.eps), factor, bool(relu))
+    return x._like(out)
+
+
+class _BatchNormTrainFn(torch.autograd.Function):
+  """BatchNorm1d(training) [+ ReLU] over the rows of a feature matrix on gclb_bn_train_fwd / gclb_bn_train_bwd."""
+
+  @staticmethod
+  def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    xc = x.detach().contiguous()
+    n, c = xc.shape
+    dev = xc.device
+    y = torch.empty_like(xc)
+    stats = torch.empty((2, c), dtype=torch.float32, device=dev)         # save_mean | save_invstd
+    sums = torch.empty((2, c), dtype=torch.float64, device=dev)
+    g = gamma.detach().contiguous() if gamma is not None else None
+    b = beta.detach().contiguous() if beta is not None else None
+    ops.call("gclb_bn_train_fwd", ops.ptr(xc), n, c, ops.ptr(g), ops.ptr(b), eps, momentum, ops.ptr(running_mean),
+             ops.ptr(running_var), int(relu), ops.ptr(y), stats[0].data_ptr(), stats[1].data_ptr(), ops.ptr(sums), ops.stream())
+    ctx.save_for_backward(xc, y if relu else None, g, stats)
+    ctx.relu = relu
+    ctx.has_affine = gamma is not None
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    xc, y, g, stats = ctx.saved_tensors
+    n, c = xc.shape
+    dy = dy.contiguous()
+    dx = torch.empty_like(xc)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=xc.device)     # dgamma | dbeta
+    sums = torch.empty((2, c), dtype=torch.float64, device=xc.device)
+    ops.call("gclb_bn_train_bwd", ops.ptr(xc), ops.ptr(dy), ops.ptr(y), n, c, ops.ptr(g), stats[0].data_ptr(), stats[1].data_ptr(),
+             int(ctx.relu), ops.ptr(dx), dgb[0].data_ptr(), dgb[1].data_ptr(), ops.ptr(sums), ops.stream())
+    return (dx, dgb[0] if ctx.has_affine else None, dgb[1] if ctx.has_affine else None, None, None, None, None, None)
+
+
+def bn_relu(norm, x: SparseTensor) -> SparseTensor:
+  """MEF.relu(norm(x)) in one launch pair (gcl_b200 extension used by gcl_b200.resunet; the oracle module has no such helper)"""
+  return norm(x, relu=True)
 
 
 class MinkowskiInstanceNorm(nn.Module):

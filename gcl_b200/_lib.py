@@ -54,6 +54,8 @@ SIGNATURES = {
     "gclb_pointwise_tail": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p]),
     "gclb_affine_act": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "gclb_bn_stats": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "gclb_bn_train_fwd": (C.c_int, [_p, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "gclb_bn_train_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "gclb_nn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i64]),
     "gclb_nn": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "gclb_subsample": (C.c_int, [_p, _p, _i64, _i32, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),

@@ -27,6 +27,8 @@ VARIANTS = {
 
 def make_models(ME):
   MEF = ME.MinkowskiFunctional
+  # norm followed by ReLU: one fused launch pair on gcl_b200.MinkowskiEngine, MEF.relu(norm(x)) on any other operator module
+  bn_relu = getattr(ME, "bn_relu", None) or (lambda norm, x: MEF.relu(norm(x)))
 
   class Block(nn.Module):
     """conv3-BN-ReLU-conv3-BN-(+x)-ReLU (residual_block.py:40-53)."""
@@ -40,7 +42,7 @@ def make_models(ME):
       self.norm2 = ME.MinkowskiBatchNorm(planes, momentum=bn_momentum)
 
     def forward(self, x):
-      y = MEF.relu(self.norm1(self.conv1(x)))
+      y = bn_relu(self.norm1, self.conv1(x))
       y = self.norm2(self.conv2(y))
       y += x
       return MEF.relu(y)

@@ -256,6 +256,20 @@ int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, co
                     const float* residual, int32_t relu, float* y, void* stream);
 /* training-mode BatchNorm statistics over all rows: sum[c], sumsq[c] as float64 (caller-zeroed) */
 int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sumsq, void* stream);
+/* MinkowskiBatchNorm in TRAINING mode (model/common.py:6 = torch.nn.BatchNorm1d over the rows of .F; forward
+ * lib/colocation_trainer.py:846, backward via loss.backward() :879), optionally fused with the MEF.relu that follows it in
+ * every residual block (model/residual_block.py:42; model/resunet.py:177-223).
+ *   forward:  y = [relu]((x - mean_batch) / sqrt(var_batch + eps) * gamma + beta), statistics over ALL n rows (biased variance);
+ *             running_mean / running_var (may be NULL) updated in place with `momentum` and the UNBIASED variance;
+ *             save_mean / save_invstd float32 [c] for the backward pass
+ *   backward: dx, dgamma, dbeta of the same op given dy (relu != 0: the ReLU mask is rebuilt from the forward output y)
+ *   x, y, dy, dx float32 [n, c], c a multiple of 4; gamma / beta may be NULL (affine=False); sums float64 [2, c] workspace */
+int gclb_bn_train_fwd(const float* x, int64_t n, int32_t c, const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, int32_t relu, float* y, float* save_mean, float* save_invstd,
+                      double* sums, void* stream);
+int gclb_bn_train_bwd(const float* x, const float* dy, const float* y, int64_t n, int32_t c, const float* gamma,
+                      const float* save_mean, const float* save_invstd, int32_t relu, float* dx, float* dgamma, float* dbeta,
+                      double* sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K4 nearest neighbour in feature space, both directions from one pass, N x M never materialised.

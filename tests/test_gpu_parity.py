@@ -503,6 +503,48 @@ def test_fp16_activation_range_is_monitored(G, net):
     e32.check_range()
 
 
+@pytest.mark.parametrize("c,relu,affine,momentum", [(32, False, True, 0.05), (64, True, True, 0.05), (256, True, True, 0.1),
+                                                   (128, False, False, 0.02), (96, True, True, None)])
+def test_batchnorm_train_kernels_vs_torch(G, c, relu, affine, momentum):
+  """a7: MinkowskiBatchNorm in training mode on libgclb200's own kernels (csrc/bn.cu) against torch.nn.BatchNorm1d on the CPU
+  (what the oracle's MinkowskiBatchNorm wraps, model/common.py:6): output, running statistics (unbiased variance, momentum,
+  cumulative average for momentum=None), num_batches_tracked and the gradients w.r.t. input, gamma and beta -- with and
+  without the fused ReLU.  fp32 arithmetic on both sides: 1e-5 relative."""
+  torch.manual_seed(c)
+  n = 5000 + c
+  x = torch.randn(n, c) * 2.0 + torch.randn(c)
+  gy = torch.randn(n, c)
+  ref = torch.nn.BatchNorm1d(c, eps=1e-5, momentum=momentum, affine=affine)
+  mod = G.ME.MinkowskiBatchNorm(c, eps=1e-5, momentum=momentum, affine=affine).to(G.dev)
+  if affine:
+    with torch.no_grad():
+      ref.weight.uniform_(0.5, 1.5); ref.bias.normal_(0, 0.3)
+    mod.bn.load_state_dict(ref.state_dict())
+  coords = torch.cat([torch.zeros(n, 1, dtype=torch.int32), torch.arange(n, dtype=torch.int32)[:, None], torch.zeros(n, 2, dtype=torch.int32)], 1)
+  for step in range(2):                      # two steps: the running statistics accumulate
+    xo = x.clone().requires_grad_(True)
+    yo = ref(xo)
+    yo = torch.relu(yo) if relu else yo
+    yo.backward(gy)
+    xg = x.clone().to(G.dev).requires_grad_(True)
+    st = G.ME.SparseTensor(xg, coordinates=coords.to(G.dev)) if step == 0 else G.ME.SparseTensor(xg, coordinate_map_key=key, coordinate_manager=mgr)
+    key, mgr = st.coordinate_map_key, st.coordinate_manager
+    out = mod(st, relu=relu) if relu else mod(st)
+    out.F.backward(gy.to(G.dev))
+    assert _rel(out.F, yo) < 1e-5
+    assert _rel(xg.grad, xo.grad) < 2e-5
+    if affine:
+      assert _rel(mod.bn.weight.grad, ref.weight.grad) < 2e-5 and _rel(mod.bn.bias.grad, ref.bias.grad) < 2e-5
+      mod.bn.weight.grad = None; mod.bn.bias.grad = None; ref.weight.grad = None; ref.bias.grad = None
+    assert _rel(mod.bn.running_mean, ref.running_mean) < 1e-5 and _rel(mod.bn.running_var, ref.running_var) < 1e-5
+    assert int(mod.bn.num_batches_tracked) == int(ref.num_batches_tracked) == step + 1
+  # eval mode afterwards uses the accumulated statistics (folded affine kernel)
+  mod.eval(); ref.eval()
+  with torch.no_grad():
+    ye = mod(G.ME.SparseTensor(x.to(G.dev), coordinate_map_key=key, coordinate_manager=mgr)).F
+  assert _rel(ye, ref(x)) < 1e-5
+
+
 @pytest.mark.parametrize("mode,w,tol", [("fp32", (16, 32, 8), 1e-4), ("tf32", (32, 64, 32), 3e-3)])
 def test_training_step_grads_vs_oracle(G, mode, w, tol):
   """conv dgrad / wgrad (stride-1, strided, transposed, 1x1) and train-mode BN through a small U-shaped net; in 'tf32'
