@@ -240,6 +240,167 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
           "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
 
 
+def cpu_train_step(samples_host, steps):
+  """oracle arm of the training workload: the same step (train-mode ResUNetBN2C forward, finest-contrastive loss, backward, SGD) on
+  the CPU restatement of the MinkowskiEngine operators, on a bounded sample of the batch"""
+  import oracle.me_cpu as OME
+  from oracle import gcl_loss as oloss, groups as ogroups
+  from gcl_b200.resunet import make_models
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  torch.manual_seed(0)
+  model = make_models(OME)["ResUNetBN2C"](**MODEL)
+  model.train()
+  opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
+  cs, lens = [], []
+  for cl, _ in samples_host:
+    for x in cl:
+      cs.append(torch.floor(torch.from_numpy(x) / VOXEL).int()); lens.append(len(x))
+  C, F = OME.utils.sparse_collate(cs, [torch.ones(len(c), 1) for c in cs])
+  off = np.cumsum([0] + lens)
+  gl, il, fl = [], [], []
+  for s, (cl, Ts) in enumerate(samples_host):
+    g, i, f = ogroups.colocation_groups(cl[0], cl[1:], Ts, 1.5 * VOXEL, 5)
+    gl.append(np.asarray(g)); il.append(np.asarray(i) + off[3 * s]); fl.append(np.asarray(f))
+  group, index, finest = np.concatenate(gl), np.concatenate(il), np.concatenate(fl)
+  starts = np.concatenate([[0], np.cumsum(group)])
+  ih = oloss.exhaustive_hash([index[starts[g]:starts[g + 1]] for g in range(len(group))], len(C))
+  rng = np.random.RandomState(0)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    opt.zero_grad()
+    Fo = model(OME.SparseTensor(F, coordinates=C)).F
+    sel = oloss.draw_selections(len(group), len(C), 256 * len(samples_host), 256 * len(samples_host), rng)
+    pos, fin, neg = oloss.group_contrastive_loss(Fo, group, index, ih, finest, *sel, square_loss=True, with_finest=True)
+    (pos + fin + neg).backward()
+    opt.step()
+  dt = time.perf_counter() - t0
+  return dict(scans_per_s=steps * len(cs) / dt, seconds=dt, cores=cores, scans=len(cs), ms_per_step=dt / steps * 1e3)
+
+
+def main_train(args):
+  """BASELINE config 4: GCL training step; whole-job scans/s = clouds of all ranks / max-over-ranks step time"""
+  rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+  workload = (f"GCL training step: {args.samples} colocated scan groups x 3 nuScenes-shape scans per GPU (voxel {VOXEL} m), ResUNetBN2C "
+              "train-mode fwd + finest-contrastive loss (positive groups + hardest negatives) + bwd + SGD; gradient all-reduce over ranks")
+  if args.impl == "reference":
+    if rank != 0:
+      return
+    from gcl_b200.training import synthetic_group_batch
+    host = synthetic_group_batch(0, 1, VOXEL)      # bounded sample: one colocated group (3 scans) per step
+    r = cpu_train_step(host, max(1, min(args.steps, 3)))
+    line = {"impl": "reference", "metric": "gcl_train_scans_per_sec", "value": round(r["scans_per_s"], 4), "unit": "scans/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "samples_per_step": 1},
+            "cpu_baseline": {"value": round(r["scans_per_s"], 4), "unit": "scans/s", "cores": r["cores"], "kind": "port",
+                             "sample": f"1 colocated group (3 scans) per step through oracle/ autograd in {r['seconds']:.1f} s"},
+            "e2e": {"value": round(r["scans_per_s"], 4), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return
+  import torch.distributed as dist
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  from gcl_b200 import _lib
+  from gcl_b200.training import GclTrainStep
+  lib = _lib.load()
+  ts = GclTrainStep(dev, rank=rank, samples=args.samples, voxel=VOXEL, conv="tf32")
+  clocks = ClockSampler(local_rank)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  seg = lambda: torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+  quiet = 0
+  for i in range(max(args.warmup, 3) + 12):        # warm up until the caching allocator stops growing
+    s0 = seg()
+    ts.step()
+    quiet = quiet + 1 if seg() == s0 else 0
+    if i >= max(args.warmup, 3) and quiet >= 3:
+      break
+
+  def timed(fn, steps):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev, dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = t.item()
+    return ms
+
+  if rank == 0:
+    clocks.start()
+  l0 = lib.gclb_kernel_launches()
+  ms = timed(lambda: ts.step(), args.steps)
+  launches = lib.gclb_kernel_launches() - l0
+  clk = clocks.stop() if rank == 0 else None
+  # end to end: the batch starts in pinned host memory every step (H2D + voxelisation + positive-group construction + pair hashes
+  # inside the timed region) and the loss comes back to the host
+  clouds = [c for cl, _ in ts.host_batch for c in cl]
+  pinned = torch.from_numpy(np.concatenate(clouds)).pin_memory()
+
+  def step_e2e():
+    ts._upload_and_group(ts.host_batch, pinned=pinned)
+    return float(ts.step().detach())
+
+  for _ in range(3):
+    step_e2e()
+  ms_e2e = timed(step_e2e, max(3, args.steps // 2)) / max(3, args.steps // 2) * args.steps
+  # ranks must hold bit-identical weights after the exchange steps
+  identical = True
+  if world > 1:
+    w = torch.cat([p.detach().reshape(-1) for p in ts.model.parameters()])
+    lo, hi = w.clone(), w.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool(torch.equal(lo, hi))
+  n_scans = torch.tensor([float(ts.n_clouds)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(n_scans, op=dist.ReduceOp.SUM)
+  total_scans = n_scans.item() * args.steps
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+      pass
+    n_param = sum(p.numel() for p in ts.model.parameters())
+    line = {"metric": "gcl_train_scans_per_sec", "value": round(total_scans / (ms * 1e-3), 2), "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands (tcgen05 fwd/dgrad/wgrad), f32 accumulate, f32 BN/loss/SGD",
+            "data": "synthetic",
+            "config": {"workload": workload, "samples_per_gpu": args.samples, "scans_per_gpu": ts.n_clouds, "voxels_rank0": ts.n_rows,
+                       "groups_rank0": int(ts.group.numel()),
+                       "parallelism": f"colocated-scan groups sharded x{world}; one NCCL AVG all-reduce of the flat gradient buffer "
+                                      f"({n_param * 4 / 1e6:.0f} MB) per step" if world > 1 else "single GPU (no collective)",
+                       "ranks_bit_identical": identical,
+                       "l2": "activations + gradients of a step (~1 GB) exceed the 126 MB L2"},
+            "e2e": {"value": round(total_scans / (ms_e2e * 1e-3), 2), "unit": "scans/s", "h2d_bytes_per_step": int(pinned.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "what": "pinned host points -> H2D -> voxelise -> positive groups + pair hashes on the GPU -> step -> loss to host"},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "per-kernel numbers of the training step: profiles/ (ncu of tools/profile_step.py --train)"}}
+    if world == 1 and not args.no_cpu_baseline:
+      from gcl_b200.training import synthetic_group_batch
+      r = cpu_train_step(synthetic_group_batch(0, 1, VOXEL), 2)
+      line["cpu_baseline"] = {"value": round(r["scans_per_s"], 4), "unit": "scans/s", "cores": r["cores"], "kind": "port",
+                              "sample": f"2 steps of 1 colocated group (3 scans) through oracle/ autograd in {r['seconds']:.1f} s"}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -250,7 +411,13 @@ def main():
   ap.add_argument("--impl", default="gcl_b200", choices=["gcl_b200", "reference"])
   ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 fp32 CUDA-core conv, 2 tcgen05 conv")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--workload", default="pairs", choices=["pairs", "train"],
+                  help="pairs = BASELINE config 2 (headline: feature extraction + matching); train = config 4 (GCL training step, "
+                       "NCCL gradient all-reduce when N > 1)")
+  ap.add_argument("--samples", type=int, default=4, help="train workload: colocated scan groups (3 scans each) per GPU per step")
   args = ap.parse_args()
+  if args.workload == "train":
+    return main_train(args)
   args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
   rank = int(os.environ.get("RANK", 0))
