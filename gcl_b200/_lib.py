@@ -60,7 +60,9 @@ SIGNATURES = {
     "gclb_nn": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "gclb_subsample": (C.c_int, [_p, _p, _i64, _i32, _i64, _i32, C.c_uint64, _p, _p, _p, _p]),
     "gclb_mutual_filter": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p]),
+    "gclb_ingest_points": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p]),
     "gclb_corr_points": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i64, _p, _p, _p]),
+    "gclb_pair_metrics": (C.c_int, [_p, _p, _p, _p, _p, _i32, _f32, _p, _p]),
     "gclb_sc2pcr_workspace_bytes": (_sz, [_i64, _i32, C.c_double]),
     "gclb_sc2pcr": (C.c_int, [_p, _p, _p, _i32, _i64, _f32, _f32, _f32, C.c_double, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "gclb_loss_workspace_bytes": (_sz, [_i64, _i64]),

@@ -548,6 +548,50 @@ __global__ void __launch_bounds__(256) corr_points_kernel(const float* __restric
   }
 }
 
+// registration / matching metrics of a batch of pairs in one launch (scripts/test_kitti.py:188-195, lib/trainer.py:406-409):
+//   out[p] = { RTE = |t_est - t_gt|, RRE in degrees = acos((trace(R_est^T R_gt) - 1) / 2) with the diagonal clamped to <= 1
+//              (the reference's numerical-stability patch, :190-191), hit ratio = mean(sqrt(|T_gt x0 - x1|^2 + 1e-6) < thresh),
+//              number of correspondences }
+__global__ void __launch_bounds__(256) pair_metrics_kernel(const float* __restrict__ T_est, const float* __restrict__ T_gt,
+                                                           const float* __restrict__ src, const float* __restrict__ tgt,
+                                                           const int64_t* __restrict__ ptr, float hit_thresh,
+                                                           float* __restrict__ out) {
+  const int p = blockIdx.x;
+  const float* E = T_est + (size_t)p * 16; const float* Gt = T_gt + (size_t)p * 16;
+  __shared__ int s_hits[8];
+  int hits = 0;
+  int64_t b = 0, e = 0;
+  if (src && ptr) {
+    b = ptr[p]; e = ptr[p + 1];
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const float x = src[i * 3], y = src[i * 3 + 1], z = src[i * 3 + 2];
+      const float dx = Gt[0] * x + Gt[1] * y + Gt[2] * z + Gt[3] - tgt[i * 3];
+      const float dy = Gt[4] * x + Gt[5] * y + Gt[6] * z + Gt[7] - tgt[i * 3 + 1];
+      const float dz = Gt[8] * x + Gt[9] * y + Gt[10] * z + Gt[11] - tgt[i * 3 + 2];
+      hits += sqrtf(dx * dx + dy * dy + dz * dz + 1e-6f) < hit_thresh ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, m);
+  if ((threadIdx.x & 31) == 0) s_hits[threadIdx.x >> 5] = hits;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int h = 0;
+    for (int q = 0; q < 8; ++q) h += s_hits[q];
+    const float tx = E[3] - Gt[3], ty = E[7] - Gt[7], tz = E[11] - Gt[11];
+    float tr = 0.f;
+    for (int d = 0; d < 3; ++d) {        // diagonal of R_est^T R_gt, each entry clamped to <= 1
+      const float v = E[0 * 4 + d] * Gt[0 * 4 + d] + E[1 * 4 + d] * Gt[1 * 4 + d] + E[2 * 4 + d] * Gt[2 * 4 + d];
+      tr += fminf(v, 1.0f);
+    }
+    float* o = out + (size_t)p * 4;
+    o[0] = sqrtf(tx * tx + ty * ty + tz * tz);
+    o[1] = acosf((tr - 1.0f) * 0.5f) * 57.29577951308232f;
+    o[2] = (e > b) ? (float)h / (float)(e - b) : 0.f;
+    o[3] = (float)(e - b);
+  }
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t sc_layout(ScParams& p, unsigned char* base) {
@@ -582,6 +626,16 @@ int gclb_corr_points(const float* xyz, const int64_t* unique_map, const int64_t*
   if (blocks > 148 * 8) blocks = 148 * 8;
   corr_points_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xyz, unique_map, sel0, sel1, a_ptr, b_ptr, idx01, n_pairs,
                                                                         src_out, tgt_out);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_pair_metrics(const float* trans_est, const float* trans_gt, const float* src_xyz, const float* tgt_xyz, const int64_t* ptr,
+                      int32_t n_pairs, float hit_thresh, float* out, void* stream) {
+  GCLB_CHECK_ARG(trans_est && trans_gt && out && n_pairs >= 1, "bad arguments");
+  GCLB_CHECK_ARG((src_xyz == nullptr) == (tgt_xyz == nullptr) && (src_xyz == nullptr || ptr), "correspondences need src, tgt and ptr");
+  pair_metrics_kernel<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(trans_est, trans_gt, src_xyz, tgt_xyz, ptr, hit_thresh, out);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -345,6 +345,17 @@ int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_row
                            float* out256, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Data ingest: velodyne records -> the point matrix K1 voxelises.
+ * Replaces lib/complement_data_loader.py:358-361 (`np.fromfile(fname, np.float32).reshape(-1, 4)[:, :3]`) and the loaders'
+ * augmentation :65-70, :753-781 (`pts @ R.T + T` per cloud in float32, then `scale * pts`).
+ *   records float32 [P, width] (width 4: x, y, z, reflectance as in a KITTI .bin, 16-byte aligned; width 3: xyz) of all clouds of a
+ *   batch, concatenated (device; gcl_b200/ingest.py reads the files into ONE pinned buffer and copies it once);
+ *   cloud_ptr int64 [n_clouds+1] (device), transforms float32 [n_clouds, 4, 4] row-major or NULL, scales float32 [n_clouds] or NULL;
+ *   xyz_out float32 [P, 3].  Without transforms / scales the output is bit-identical to the reference's slice. */
+int gclb_ingest_points(const float* records, int64_t P, int32_t width, const int64_t* cloud_ptr, int32_t n_clouds,
+                       const float* transforms, const float* scales, float* xyz_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * SC2-PCR registration from putative correspondences, batched over independent problems (scan pairs).
  * Replaces Matcher.SC2_PCR, /root/reference/scripts/SC2_PCR/SC2_PCR.py:304-381 (with pick_seeds :34-58, cal_seed_trans
  * :60-168, cal_leading_eigenvector :170-196, post_refinement :235-274 and common.py:7-45 rigid_transform_3d), called right
@@ -358,6 +369,12 @@ int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_row
  *   workspace: gclb_sc2pcr_workspace_bytes(n_max, n_problems, ratio)
  * Equal scores resolve to the smaller index (torch.argsort leaves ties unspecified); rotations come from Horn's quaternion
  * form of the weighted Kabsch problem (same optimum as the SVD with the det correction). */
+/* Evaluation metrics of a batch of registered pairs in one launch: scripts/test_kitti.py:188-195 (RTE, RRE with the
+ * reference's clamp of the trace diagonal) and lib/trainer.py:406-409 (evaluate_hit_ratio on the correspondences).
+ *   trans_est, trans_gt float32 [n_pairs, 4, 4]; src_xyz / tgt_xyz float32 [sum n, 3] + ptr int64 [n_pairs+1] (device) or all NULL;
+ *   out float32 [n_pairs, 4] = RTE (m), RRE (degrees; NaN where the reference's arccos is NaN), hit ratio, #correspondences */
+int gclb_pair_metrics(const float* trans_est, const float* trans_gt, const float* src_xyz, const float* tgt_xyz, const int64_t* ptr,
+                      int32_t n_pairs, float hit_thresh, float* out, void* stream);
 size_t gclb_sc2pcr_workspace_bytes(int64_t n_max, int32_t n_problems, double ratio);
 /* the putative correspondences of a matched batch as coordinates (Matcher.match_pair's return, SC2_PCR.py:297-302), straight
  * from the outputs of gclb_subsample / gclb_nn: row i of segment p = (xyz[unique_map[sel0[i]]], xyz[unique_map[sel1[b_ptr[p] +

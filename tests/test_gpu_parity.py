@@ -952,3 +952,44 @@ def test_group_loss_honours_upstream_gradients(G):
   with pytest.raises(GclbError):
     crit.finest_contrastive_loss(Fg2.detach(), torch.from_numpy(sizes), torch.from_numpy(index), ih, torch.from_numpy(bad),
                                  selections=(np.arange(len(sizes)), sel[1], sel[2]))
+
+
+def test_ingest_velodyne_bin_files(G, tmp_path):
+  """f3: KITTI .bin reader -> pinned buffer -> one H2D -> gclb_ingest_points, against the reference's
+  `np.fromfile(fname, dtype=np.float32).reshape(-1, 4)[:, :3]` (lib/complement_data_loader.py:358-361): bit-identical without
+  augmentation; with the loaders' random rotation + scale (:65-70, :753-781, float32 numpy) within 1e-6 relative (BLAS may fuse
+  the multiply-adds), and the voxelisation downstream equals the oracle's on the ingested points"""
+  from gcl_b200 import ingest
+  rng = np.random.RandomState(3)
+  paths, clouds = [], []
+  for i, n in enumerate((12345, 1, 40000)):
+    xyz = (rng.randn(n, 3) * [30, 30, 2]).astype(np.float32)
+    p = str(tmp_path / f"{i:06d}.bin")
+    ingest.write_velodyne_bin(p, xyz, rng.rand(n).astype(np.float32))
+    paths.append(p); clouds.append(xyz)
+  reader = ingest.ScanReader(capacity_points=60000)
+  rec, ptr = reader.read(paths)
+  assert rec.is_pinned() and ptr.tolist() == [0, 12345, 12346, 52346]
+  want = np.concatenate([np.fromfile(p, dtype=np.float32).reshape(-1, 4)[:, :3] for p in paths])
+  got = ingest.points_to_device(rec, ptr, G.dev)
+  assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), want)
+  cm, umap = G.ops.voxelize(got, 0.3, ptr)
+  C_ref, sel_ref = _oracle_voxelize([want[ptr[i]:ptr[i + 1]] for i in range(3)], 0.3)
+  assert torch.equal(cm.coords.cpu(), C_ref) and torch.equal(umap.cpu(), sel_ref)
+  # augmentation path
+  Ts, scales, ref = [], [], []
+  for i in range(3):
+    a = rng.uniform(-np.pi / 4, np.pi / 4)
+    T = np.eye(4); T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]; T[:3, 3] = rng.randn(3)
+    sc = 0.8 + 0.4 * rng.rand()
+    t32 = T.astype(np.float32)
+    pts = clouds[i] @ t32[:3, :3].T + t32[:3, 3]              # apply_transform (:65-70)
+    ref.append(np.float32(sc) * pts); Ts.append(T); scales.append(sc)
+  got = ingest.points_to_device(rec, ptr, G.dev, transforms=Ts, scales=scales).cpu().numpy()
+  ref = np.concatenate(ref)
+  assert np.abs(got - ref).max() <= 1e-6 * np.abs(ref).max() + 1e-6
+  # a truncated file is refused loudly
+  with open(paths[0], "ab") as f:
+    f.write(b"\x00\x00")
+  with pytest.raises(Exception):
+    reader.read(paths)

@@ -101,3 +101,28 @@ def test_pair_hashes_vs_reference_golden():
   assert np.array_equal(oloss.neg_hash(g["neg_i1"], g["neg_i2"], int(g["neg_M"])), g["neg_keys"])
   loss = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gcl_loss.npz"))
   assert np.array_equal(loss["index_hash"], g["c2_keys"])
+
+
+def test_hardest_contrastive_oracle_vs_reference_golden():
+  """f4: oracle/metrics.hardest_contrastive against values + gradients produced by the reference's own
+  HardestContrastiveLossTrainer.contrastive_hardest_negative_loss (tests/golden/make_golden_metrics.py)"""
+  from oracle import metrics as omet
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hardest_loss.npz"))
+  a, b = torch.from_numpy(g["F0"]).requires_grad_(True), torch.from_numpy(g["F1"]).requires_grad_(True)
+  pos, neg = omet.hardest_contrastive(a, b, g["pairs"], g["sel0"], g["sel1"], g["pos_sel"])
+  (pos + neg).backward()
+  assert abs(float(pos) - g["losses"][0]) < 1e-6 and abs(float(neg) - g["losses"][1]) < 1e-6
+  assert np.abs(a.grad.numpy() - g["g0"]).max() < 1e-7 and np.abs(b.grad.numpy() - g["g1"]).max() < 1e-7
+
+
+def test_metric_formulas_known_answers():
+  from oracle import metrics as omet
+  T = torch.eye(4)
+  E = torch.eye(4)
+  ang = np.deg2rad(3.0)
+  E[:3, :3] = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
+  E[:3, 3] = torch.tensor([0.3, 0.4, 0.0])
+  rte, rre = omet.rte_rre(E, T)
+  assert abs(rte - 0.5) < 1e-6 and abs(np.rad2deg(rre) - 3.0) < 1e-3
+  x = torch.randn(100, 3)
+  assert omet.evaluate_hit_ratio(x, x @ E[:3, :3].t() + E[:3, 3], E, 0.1) == 1.0
