@@ -47,12 +47,16 @@ def seeded_model(ME, seed=0):
   return m.eval()
 
 
-def make_batches(n_batches, pairs_per_batch, seed, n_base=3):
+SENSOR = {"name": "KITTI"}      # set by --workload nuscenes
+
+
+def make_batches(n_batches, pairs_per_batch, seed, n_base=6):
   """Host-side synthetic input: `n_base` ray-cast LoKITTI-style pairs; every batch entry is one of them under a fresh
   random yaw + translation (applied to both scans of the pair), so voxelisation differs in every batch."""
   from gcl_b200 import synth
   rng = np.random.RandomState(seed)
-  base = [synth.scan_pair(scene_seed=seed * 7 + i, pair_seed=seed * 13 + i) for i in range(n_base)]
+  sensor = synth.NUSCENES if SENSOR["name"] == "NUSCENES" else synth.KITTI
+  base = [synth.scan_pair(scene_seed=seed * 7 + i, pair_seed=seed * 13 + i, sensor=sensor) for i in range(n_base)]
   batches = []
   for b in range(n_batches):
     clouds = []
@@ -226,9 +230,13 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
   peak = peaks.get("hbm_gbs", 6650.0)
   ach = tot_b / (tot_ms * 1e-3) / 1e9
   traffic, traffic_src = None, None
-  try:   # DRAM bytes per launch of the same kernels from the committed ncu capture of this build (never measured here)
-    tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v24_conv_traffic.json")))
-    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+  try:   # DRAM bytes per launch of the same kernels from an ncu capture -- accepted only if it was taken from THIS build
+    from gcl_b200 import build as _b
+    tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+    if tj.get("build_id") == _b.source_id():
+      traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    else:
+      traffic_src = f"profiles/conv_traffic.json is stale (build {tj.get('build_id')} != {_b.source_id()}): not reported"
   except Exception:
     pass
   return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
@@ -276,6 +284,101 @@ def cpu_train_step(samples_host, steps):
     opt.step()
   dt = time.perf_counter() - t0
   return dict(scans_per_s=steps * len(cs) / dt, seconds=dt, cores=cores, scans=len(cs), ms_per_step=dt / steps * 1e3)
+
+
+def main_sweep(args):
+  """BASELINE config 5: voxel-size sweep 0.1-0.5 m on a dense synthetic surface (6 M points): per voxel size one step = K1 voxelise +
+  strided / kernel maps + ResUNetBN2C forward of the whole cloud; reported as Mvoxels/s per size, `value` = the 0.1 m (~1 M voxel) case"""
+  rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+  workload = "voxel-size sweep 0.1-0.5 m on a dense synthetic surface (6M points): voxelise + maps + ResUNetBN2C(k5,32-d) forward per size"
+  if args.impl == "reference":
+    if rank != 0:
+      return
+    import oracle.me_cpu as OME
+    from gcl_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = seeded_model(OME)
+    pts = torch.from_numpy(synth.dense_surface(300_000, seed=3))      # bounded sample: 1/20 of the points, 0.3 m voxels
+    t0 = time.perf_counter()
+    nv = 0
+    for _ in range(max(1, min(args.steps, 3))):
+      _, sel = OME.utils.sparse_quantize(pts / 0.3, return_index=True)
+      c = torch.floor(pts[sel] / 0.3).int()
+      C, F = OME.utils.sparse_collate([c], [torch.ones(len(c), 1)])
+      with torch.no_grad():
+        model(OME.SparseTensor(F, coordinates=C))
+      nv += len(c)
+    dt = time.perf_counter() - t0
+    v = nv / dt / 1e6
+    print(json.dumps({"impl": "reference", "metric": "mvoxels_per_sec", "value": round(v, 4), "unit": "Mvoxels/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / max(1, min(args.steps, 3)) * 1e3, 1),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": workload, "sample": "300k points at 0.3 m through oracle/"},
+                      "cpu_baseline": {"value": round(v, 4), "unit": "Mvoxels/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"300k-point surface at 0.3 m voxels through oracle/ in {dt:.1f} s"},
+                      "e2e": {"value": round(v, 4), "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return
+  import torch.distributed as dist
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  from gcl_b200 import MinkowskiEngine as ME, _lib, synth
+  from gcl_b200.engine import ResUNetEngine
+  lib = _lib.load()
+  eng = ResUNetEngine(seeded_model(ME), device=dev)
+  pts_h = torch.from_numpy(synth.dense_surface(6_000_000, seed=3 + rank)).pin_memory()
+  pts = pts_h.to(dev)
+  sizes = (0.1, 0.2, 0.3, 0.5)
+  res, total_ms, total_vox, launches = {}, 0.0, 0, 0
+  clocks = ClockSampler(local_rank)
+  if rank == 0:
+    clocks.start()
+  for vs in sizes:
+    for _ in range(max(args.warmup, 3)):
+      eng.extract(pts, vs)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    l0 = lib.gclb_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nv = 0
+    for _ in range(args.steps):
+      f, cm, _ = eng.extract(pts, vs)
+      nv += cm.n
+    float(f[0, 0])                               # D2H of a result element: the step's output is consumed
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches += lib.gclb_kernel_launches() - l0
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(max(2, args.steps // 4)):
+      f, cm, _ = eng.extract(pts_h.to(dev, non_blocking=True), vs)
+      f[:16].cpu()
+    e3.record()
+    torch.cuda.synchronize()
+    ms_e2e = e2.elapsed_time(e3) / max(2, args.steps // 4)
+    if world > 1:
+      t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, ms_e2e = t.tolist()
+    res[str(vs)] = {"voxels": nv // args.steps, "ms_per_step": round(ms / args.steps, 3),
+                    "mvoxels_per_sec": round(world * nv / (ms * 1e-3) / 1e6, 2), "e2e_mvoxels_per_sec": round(world * cm.n / (ms_e2e * 1e-3) / 1e6, 2)}
+    total_ms += ms; total_vox += nv
+  clk = clocks.stop() if rank == 0 else None
+  if rank == 0:
+    big = res["0.1"]
+    print(json.dumps({"metric": "mvoxels_per_sec", "value": big["mvoxels_per_sec"], "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": big["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+                      "config": {"workload": workload, "headline_case": f"voxel 0.1 m, {big['voxels']} voxels", "per_voxel_size": res,
+                                 "l2": "the 0.1 m case moves ~4 GB of activations per forward (>> 126 MB L2)"},
+                      "e2e": {"value": big["e2e_mvoxels_per_sec"], "unit": "Mvoxels/s", "h2d_bytes_per_step": int(pts_h.numel() * 4),
+                              "d2h_bytes_per_step": 16 * 32 * 4}, "gpu_launches": int(launches), "clocks": clk,
+                      "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                                   "note": "per-kernel roofline: the pairs workload (same kernels)"}}))
+  if world > 1:
+    dist.destroy_process_group()
 
 
 def main_train(args):
@@ -411,19 +514,27 @@ def main():
   ap.add_argument("--impl", default="gcl_b200", choices=["gcl_b200", "reference"])
   ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 fp32 CUDA-core conv, 2 tcgen05 conv")
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--workload", default="pairs", choices=["pairs", "train"],
-                  help="pairs = BASELINE config 2 (headline: feature extraction + matching); train = config 4 (GCL training step, "
-                       "NCCL gradient all-reduce when N > 1)")
+  ap.add_argument("--workload", default="pairs", choices=["pairs", "nuscenes", "sweep", "train"],
+                  help="pairs = BASELINE config 2 (headline: feature extraction + matching on KITTI-shape pairs); nuscenes = config 3 "
+                       "(32-beam scans, 8 pairs per step); sweep = config 5 (voxel-size sweep on a dense surface, up to ~1M voxels); "
+                       "train = config 4 (GCL training step, NCCL gradient all-reduce when N > 1)")
   ap.add_argument("--samples", type=int, default=4, help="train workload: colocated scan groups (3 scans each) per GPU per step")
   args = ap.parse_args()
   if args.workload == "train":
     return main_train(args)
+  if args.workload == "sweep":
+    return main_sweep(args)
+  if args.workload == "nuscenes":
+    SENSOR["name"] = "NUSCENES"
+    if args.pairs == 16:
+      args.pairs = 8                       # BASELINE config 3: batch of 8 pairs = 16 clouds
   args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
   rank = int(os.environ.get("RANK", 0))
   world = int(os.environ.get("WORLD_SIZE", 1))
   local_rank = int(os.environ.get("LOCAL_RANK", 0))
-  workload = (f"LoKITTI-style synthetic scan pairs (64-beam ~130k pts/scan, voxel {VOXEL} m): voxelise + kernel maps + "
+  shape = "nuScenes-shape 32-beam ~33k pts/scan" if SENSOR["name"] == "NUSCENES" else "64-beam ~130k pts/scan"
+  workload = (f"LoKITTI-style synthetic scan pairs ({shape}, voxel {VOXEL} m): voxelise + kernel maps + "
               f"ResUNetBN2C(k5,32-d) fwd x2 + {SUBSAMPLE}-pt subsample + mutual-NN")
 
   if args.impl == "reference":
@@ -576,6 +687,51 @@ def main():
   ms_reg, _ = timed_region(step_registered, reg_steps, resident)
   matcher.do_register = False
 
+  # end to end FROM FILE BYTES: every cloud is a KITTI-layout .bin (float32 x, y, z, reflectance) on local storage;
+  # per step: read the files into the pinned staging buffer -> one H2D -> gclb_ingest_points -> the same path -> D2H
+  import tempfile
+  from gcl_b200 import ingest
+  tmpdir = tempfile.mkdtemp(prefix=f"gclb_bench_r{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+  file_batches = []
+  for b, (x, p) in enumerate(host):
+    pl = p.tolist()
+    paths = []
+    for c in range(len(pl) - 1):
+      fn = os.path.join(tmpdir, f"b{b}_{c:03d}.bin")
+      ingest.write_velodyne_bin(fn, x[pl[c]:pl[c + 1]].numpy())
+      paths.append(fn)
+    file_batches.append(paths)
+  readers = [ingest.ScanReader(capacity_points=max(x.shape[0] for x, _ in host) + 1024) for _ in range(max(args.depth, 1) + 1)]
+
+  def disk_source(n):
+    for i in range(n):
+      rec, ptr = readers[i % len(readers)].read(file_batches[i % n_batches])
+      yield ingest.points_to_device(rec, ptr, dev), ptr
+
+  def run_disk(steps):
+    nv = 0
+    if args.depth > 1:
+      for s_, out in enumerate(matcher.match_many(disk_source(steps), depth=args.depth)):
+        nv += step_e2e(s_, out)
+    else:
+      for s_, (xd, ptr) in enumerate(disk_source(steps)):
+        nv += step_e2e(s_, matcher.match(xd, ptr))
+    return nv
+
+  for _ in range(2):
+    run_disk(n_batches * max(args.depth, 1))
+  barrier()
+  ed0, ed1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ed0.record()
+  run_disk(args.steps)
+  ed1.record()
+  barrier()
+  ms_disk = ed0.elapsed_time(ed1)
+  if world > 1:
+    t = torch.tensor([ms_disk], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_disk = t.item()
+  import shutil
+  shutil.rmtree(tmpdir, ignore_errors=True)
+
   total_pairs = args.pairs * args.steps * world
   value = total_pairs / (ms * 1e-3)
   e2e_value = total_pairs / (ms_e2e * 1e-3)
@@ -597,6 +753,9 @@ def main():
                                    if (lib.gclb_has_tcgen05() and args.algo != 1) else "fp32 CUDA-core implicit GEMM")},
           "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(ms_e2e / args.steps, 3)},
+          "e2e_from_disk": {"value": round(total_pairs / (ms_disk * 1e-3), 2), "unit": "pairs/s", "ms_per_step": round(ms_disk / args.steps, 3),
+                            "file_bytes_per_step": int(np.mean([x.shape[0] * 16 for x, _ in host])),
+                            "what": "KITTI-layout .bin files (tmpfs) -> readinto pinned buffer -> H2D -> gclb_ingest_points -> same path -> D2H"},
           "registered": {"metric": "registered_scan_pairs_per_sec", "value": round(args.pairs * reg_steps * world / (ms_reg * 1e-3), 2),
                          "unit": "pairs/s", "ms_per_step": round(ms_reg / reg_steps, 3), "steps": reg_steps,
                          "what": "same step + SC2-PCR registration of every pair on the GPU (5000 putative correspondences per pair, "

@@ -20,6 +20,17 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
          "--expt-relaxed-constexpr"]
 
 
+def source_id() -> str:
+  """short hash of every CUDA source + header of the library: identifies the build an ncu capture / profile belongs to"""
+  import hashlib
+  h = hashlib.sha1()
+  files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+  for f in files + [os.path.join(os.path.dirname(HERE), "include", "gclb200.h")]:
+    with open(f if os.path.isabs(f) else os.path.join(CSRC, f), "rb") as fh:
+      h.update(fh.read())
+  return h.hexdigest()[:12]
+
+
 def sources():
   return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
