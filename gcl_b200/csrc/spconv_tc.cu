@@ -18,6 +18,7 @@
 // Every output row is produced by exactly one CTA: no atomics, bit-reproducible.
 // All mbarrier waits are bounded spins that trap on a protocol bug instead of hanging the GPU.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "tc_epilogue.cuh"
@@ -29,21 +30,30 @@ constexpr int KSLAB = 32;             // tf32: channels per stage = one 128-byte
 //                1 = fp16 activations, kind::f16,  64 channels per 128-byte row (SWIZZLE_128B)
 //                2 = fp16 activations, kind::f16,  32 channels per  64-byte row (SWIZZLE_64B): sources whose width is a
 //                    multiple of 32 but not of 64 (the 32-channel stride-1 level of the ResUNet)
-constexpr int kGatherWarps = 8;
-constexpr int kMmaWarp = 8, kNbrWarp = 9;
-constexpr int kTcThreads = 14 * 32;   // 448: warps 10-13 are the epilogue
+// CTAS = CTAs per SM.  1: the original layout (8 gather warps | MMA | nbr | 4 epilogue = 448 threads, the whole shared memory).
+// 2: two independent half-size CTAs per SM (4 gather warps | MMA | nbr | 4 epilogue = 320 threads, half the ring each).  The cycle
+// accounting of round 2 (profiles/r02_conv_ablation.md) showed the kernel bound by the serial latency chains of its roles -- one
+// thread issuing a tcgen05.mma every ~100 cycles, barrier round trips, the epilogue of a tile -- not by a throughput resource:
+// with no data movement at all it still took 85 % of its time.  Two CTAs per SM interleave two such chains on the same SM.
+template <int CTAS> struct TcRoles {
+  static constexpr int kGatherWarps = CTAS == 2 ? 4 : 8;
+  static constexpr int kMmaWarp = kGatherWarps, kNbrWarp = kGatherWarps + 1, kEpiWarp0 = kGatherWarps + 2;
+  static constexpr int kThreads = (kGatherWarps + 6) * 32;     // 448 / 320
+};
 
-template <int COUT, int MODE = 0>
+template <int COUT, int MODE = 0, int CTAS = 1>
 struct TcCfg {
   static constexpr int ROWB = MODE == 2 ? 64 : 128;       // bytes per operand row
   static constexpr int A_BYTES = TM * ROWB;               // 16 KB / 8 KB
   static constexpr int B_BYTES = COUT * ROWB;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  // deepest ring that leaves room for two neighbour tiles (2 x 14 KB) in 227 KB
-  static constexpr int STAGES = COUT >= 256 ? 4 : (COUT >= 128 ? 5 : (COUT >= 64 ? 7 : 8));
-  static constexpr int NBUF = COUT >= 256 ? 2 : 4;                // neighbour-tile ring (tiles prefetched ahead)
-  static constexpr int NACC = COUT >= 256 ? 2 : 4;                // TMEM accumulator ring (tiles the MMA may run ahead)
-  static constexpr int TMEM_COLS = NACC * COUT;                   // 128 / 256 / 512 / 512 columns (powers of two)
+  // CTAS == 1: deepest ring that leaves room for two neighbour tiles (2 x 14 KB) in 227 KB; CTAS == 2: ~112 KB and 256 TMEM
+  // columns per CTA
+  static constexpr int STAGES = CTAS == 2 ? (COUT >= 128 ? 2 : (STAGE > 16384 ? 3 : 4))
+                                          : (COUT >= 256 ? 4 : (COUT >= 128 ? 5 : (COUT >= 64 ? 7 : 8)));
+  static constexpr int NBUF = (CTAS == 2 || COUT >= 256) ? 2 : 4;  // neighbour-tile ring (tiles prefetched ahead)
+  static constexpr int NACC = CTAS == 2 ? (COUT >= 128 ? 2 : 4) : (COUT >= 256 ? 2 : 4);   // TMEM accumulator ring
+  static constexpr int TMEM_COLS = NACC * COUT;                   // powers of two; <= 256 per CTA when two share an SM
 };
 
 struct TcShared {   // static shared: barriers + small per-tile metadata
@@ -56,11 +66,12 @@ struct TcShared {   // static shared: barriers + small per-tile metadata
   int act_k[4][32];
 };
 
-template <int COUT, int KVOL, int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
+template <int COUT, int KVOL, int MODE, int CTAS>
+__global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
                                                                       const __grid_constant__ CUtensorMap map0,
                                                                       const __grid_constant__ CUtensorMap map1) {
-  using Cfg = TcCfg<COUT, MODE>;
+  using Cfg = TcCfg<COUT, MODE, CTAS>;
+  constexpr int kGatherWarps = TcRoles<CTAS>::kGatherWarps, kMmaWarp = TcRoles<CTAS>::kMmaWarp, kNbrWarp = TcRoles<CTAS>::kNbrWarp;
   constexpr bool HALF = MODE != 0;
   constexpr int A_BYTES = Cfg::A_BYTES;
   constexpr int ROWB = Cfg::ROWB;
@@ -303,23 +314,23 @@ __global__ void __launch_bounds__(256) weights_to_tc_f16_kernel(const float* __r
   }
 }
 
-template <int COUT, int KVOL, int MODE>
-static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
-  using Cfg = TcCfg<COUT, MODE>;
+template <int COUT, int KVOL, int MODE, int CTAS>
+static int launch_tc_n(const ConvParams& p, int64_t n_in, cudaStream_t st) {
+  using Cfg = TcCfg<COUT, MODE, CTAS>;
   size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
-  auto kern = spconv_fwd_tc_kernel<COUT, KVOL, MODE>;
+  auto kern = spconv_fwd_tc_kernel<COUT, KVOL, MODE, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return GCLB_ERR_CUDA;
   }
   const int num_tiles = (int)((p.n_out + TM - 1) / TM);
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;     // persistent: one CTA per SM
+  const int grid = num_tiles < kNumSMs * CTAS ? num_tiles : kNumSMs * CTAS;     // persistent: CTAS CTAs per SM
   CUtensorMap map0, map1;
   int rc = make_rows_tensor_map_ex(&map0, p.in0, n_in, p.c0, MODE, false);
   if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, MODE, false) : (map1 = map0, GCLB_OK);
   if (rc != GCLB_OK) return rc;
-  kern<<<grid, kTcThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
+  kern<<<grid, TcRoles<CTAS>::kThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: CUDA error: %s", cudaGetErrorString(e));
@@ -327,6 +338,18 @@ static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   }
   count_launches(1);
   return GCLB_OK;
+}
+
+template <int COUT, int KVOL, int MODE>
+static int launch_tc(const ConvParams& p, int64_t n_in, cudaStream_t st) {
+  // GCLB_TC_CTAS=2 selects two half-size CTAs per SM (COUT <= 128).  Measured on B200 (16-pair step, 641 k rows): 64->64
+  // 194.8 vs 201.3 us, 32->32 173.3 vs 175.7 us, 128->128 392 vs 346 us (its ring shrinks to 2 stages) -- no net gain, so the
+  // single-CTA layout stays the default; the variant is kept for A/B measurements (profiles/r02_conv_ablation.md)
+  static const int want = getenv("GCLB_TC_CTAS") ? atoi(getenv("GCLB_TC_CTAS")) : 1;
+  if constexpr (COUT <= 128) {
+    if (want == 2) return launch_tc_n<COUT, KVOL, MODE, 2>(p, n_in, st);
+  }
+  return launch_tc_n<COUT, KVOL, MODE, 1>(p, n_in, st);
 }
 
 bool spconv_tc_supported(const ConvParams& p) {
