@@ -105,7 +105,9 @@ def ptr(t):
 
 
 def stream():
-  return torch.cuda.current_stream().cuda_stream
+  # the raw handle of torch's current stream; torch.cuda.current_stream() builds a Python Stream object per call (~15 us,
+  # 180 launches per training step), the C accessor is ~0.3 us
+  return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def call(name, *args):

@@ -85,15 +85,43 @@ class GroupContrastiveLoss:
     self.weights = (float(pos_weight), float(finest_weight), float(neg_weight))
     self.rng = rng
 
+  def prepare(self, group, index, index_hash, finest_flag, device):
+    """Batch-dependent (step-independent) inputs of the loss on the device: CSR of the groups, position of the finest member of
+    every group, sorted positive-pair keys.  The colocation loaders produce these once per batch (the reference builds
+    `index_hash` in its collate function); the trainer passes the result as `prepared=` and the per-step work is the kernels."""
+    dev = torch.device(device)
+    on_dev = isinstance(group, torch.Tensor) and group.is_cuda
+    g = torch.as_tensor(group).to(device=dev, dtype=torch.int64)
+    G = g.numel()
+    if G == 0:
+      raise _lib.GclbError("group sizes must be >= 1 and there must be at least one group")
+    group_ptr = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+    group_ptr[1:] = torch.cumsum(g, 0)
+    index_d = torch.as_tensor(index).to(device=dev, dtype=torch.int64).contiguous()
+    ff = torch.as_tensor(finest_flag).to(device=dev, dtype=torch.bool)
+    pos_in_group = torch.arange(ff.numel(), device=dev) - torch.repeat_interleave(group_ptr[:-1], g)
+    gid = torch.repeat_interleave(torch.arange(G, device=dev), g)
+    big = torch.full((G,), 1 << 30, dtype=torch.int64, device=dev)
+    big.scatter_reduce_(0, gid[ff], pos_in_group[ff], reduce="amin")          # FIRST True inside each group (:484)
+    keys = torch.as_tensor(index_hash if isinstance(index_hash, torch.Tensor) else np.asarray(index_hash), dtype=torch.int64)
+    keys = torch.sort(keys.to(dev)).values.contiguous()
+    if not on_dev:   # host inputs: validate like the reference would fail (IndexError on an empty finest selection, :484)
+      if bool((g < 1).any()):
+        raise _lib.GclbError("group sizes must be >= 1 and there must be at least one group")
+    return dict(group_ptr=group_ptr, index=index_d, finest_big=big, keys=keys, G=G, validated=False)
+
   def _run(self, F_out, group, index, index_hash, finest_flag, max_pos_cluster, max_hn_samples, square,
-           with_finest, selections=None):
+           with_finest, selections=None, prepared=None):
     if not F_out.is_cuda:
       raise _lib.GclbError("GroupContrastiveLoss runs on CUDA tensors only (no CPU fallback)")
     dev = F_out.device
     N = len(F_out)
-    group_h = torch.as_tensor(group).cpu().to(torch.int64)
-    G = len(group_h)
+    prep = prepared if prepared is not None else self.prepare(group, index, index_hash, finest_flag, dev)
+    G = prep["G"]
     if selections is None:
+      # the reference's calls in the reference's order (:456-459, :506-507).  With a legacy RandomState each `choice(N, k,
+      # replace=False)` permutes all N rows (2 ms at N = 120k); a numpy Generator (rng=np.random.default_rng(seed)) draws the
+      # same distribution in O(k)
       if G > max_pos_cluster:
         pos_sel = self.rng.choice(G, max_pos_cluster, replace=False)
       else:
@@ -102,37 +130,33 @@ class GroupContrastiveLoss:
       sel2 = self.rng.choice(N, min(N, max_hn_samples), replace=False)
     else:
       pos_sel, sel1, sel2 = selections
-    if G == 0 or bool((group_h < 1).any()):
-      raise _lib.GclbError("group sizes must be >= 1 and there must be at least one group")
-    group_ptr = torch.zeros(G + 1, dtype=torch.int64)
-    group_ptr[1:] = torch.cumsum(group_h, 0)
-    index_d = torch.as_tensor(index).to(device=dev, dtype=torch.int64).contiguous()
+    sels = np.concatenate([np.asarray(pos_sel, np.int64), np.asarray(sel1, np.int64), np.asarray(sel2, np.int64)])
+    sels_d = torch.from_numpy(sels).pin_memory().to(dev, non_blocking=True)      # one small H2D for the three selections
+    n0, n1 = len(pos_sel), len(sel1)
+    pos_sel_d, sel1_d, sel2_d = sels_d[:n0], sels_d[n0:n0 + n1], sels_d[n0 + n1:]
     finest_pos = None
     if with_finest:
-      ff = torch.as_tensor(finest_flag).cpu().to(torch.bool)
-      # position of the FIRST True inside each group (reference: feature_set[finest_flag_set][0])
-      pos_in_group = torch.arange(len(ff)) - torch.repeat_interleave(group_ptr[:-1], group_h)
-      big = torch.full((G,), 1 << 30, dtype=torch.int64)
-      gid = torch.repeat_interleave(torch.arange(G), group_h)
-      big.scatter_reduce_(0, gid[ff], pos_in_group[ff], reduce="amin")
-      sel_groups = torch.as_tensor(np.asarray(pos_sel), dtype=torch.int64)
-      if bool((big[sel_groups] >= (1 << 30)).any()):
-        # the reference raises IndexError here (`feature_set[finest_flag_set][0]` on an empty selection, :484)
-        raise _lib.GclbError("finest_contrastive_loss: a selected group has no member with finest_flag set")
-      finest_pos = big.clamp_(max=(1 << 30) - 1).to(torch.int32).to(dev)
-    keys = torch.sort(torch.as_tensor(np.asarray(index_hash), dtype=torch.int64).to(dev)).values.contiguous()
-    to_d = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64).to(dev).contiguous()
-    args = (group_ptr.to(dev), index_d, finest_pos, to_d(pos_sel), to_d(sel1), to_d(sel2), keys,
+      big = prep["finest_big"]
+      if not prep["validated"]:
+        # a selected group without a finest member: the reference raises IndexError (`feature_set[finest_flag_set][0]`, :484).
+        # One host read per prepared batch (every group is checked, so later selections need no further check).
+        if bool((big >= (1 << 30)).any()):
+          if bool((big[pos_sel_d] >= (1 << 30)).any()):
+            raise _lib.GclbError("finest_contrastive_loss: a selected group has no member with finest_flag set")
+        else:
+          prep["validated"] = True
+      finest_pos = big.clamp(max=(1 << 30) - 1).to(torch.int32)
+    args = (prep["group_ptr"], prep["index"], finest_pos, pos_sel_d, sel1_d, sel2_d, prep["keys"],
             (self.pos_thresh, self.finest_thresh, self.neg_thresh), square)
     return _GroupLossFn.apply(F_out, args)
 
   def finest_contrastive_loss(self, F_out, group, index, index_hash, finest_flag, max_pos_cluster=256,
-                              max_hn_samples=2048, points=None, batch_lengths=None, selections=None):
+                              max_hn_samples=2048, points=None, batch_lengths=None, selections=None, prepared=None):
     return self._run(F_out, group, index, index_hash, finest_flag, max_pos_cluster, max_hn_samples,
-                     self.square_loss, True, selections)
+                     self.square_loss, True, selections, prepared)
 
   def location_contrastive_loss(self, F_out, group, index, index_hash, finest_flag, max_pos_cluster=256,
-                                max_hn_samples=None, points=None, batch_lengths=None, selections=None):
+                                max_hn_samples=None, points=None, batch_lengths=None, selections=None, prepared=None):
     pos, _, neg = self._run(F_out, group, index, index_hash, finest_flag, max_pos_cluster, max_hn_samples, False,
-                            False, selections)
+                            False, selections, prepared)
     return pos, torch.zeros((), device=F_out.device), neg

@@ -62,7 +62,7 @@ class GclTrainStep:
     self.model.train()
     self.opt = torch.optim.SGD(self.model.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
     self.crit = GroupContrastiveLoss(pos_thresh=0.1, neg_thresh=1.4, finest_thresh=0.2, square_loss=True,
-                                     rng=np.random.RandomState(0))
+                                     rng=np.random.default_rng(0))
     self.grads = FlatGradients(self.model.parameters())
 
   def _upload_and_group(self, host_batch, pinned=None):
@@ -92,15 +92,16 @@ class GclTrainStep:
     self.index_hash = gg.exhaustive_hash(self.group, self.index, self.n_rows)
     self.feats = torch.ones(self.n_rows, 1, device=dev)
     self.h2d_bytes = int(xyz.numel() * 4)
-    # host mirrors of what the loss wrapper wants on the host (group sizes, flags, pair hashes), made once per batch
-    self.group_h, self.finest_h, self.index_hash_h = self.group.cpu(), self.finest.cpu(), self.index_hash.cpu().numpy()
+    self.prepared = None     # per-batch loss inputs (CSR, finest positions, sorted pair keys): built on the device, once
 
   def step(self):
     self.grads.zero()
     st = ME.SparseTensor(self.feats, coordinates=self.cm.coords)
     F = self.model(st).F
-    pos, fin, neg = self.crit.finest_contrastive_loss(F, self.group_h, self.index, self.index_hash_h, self.finest_h,
-                                                      max_pos_cluster=256 * self.samples, max_hn_samples=256 * self.samples)
+    if self.prepared is None:
+      self.prepared = self.crit.prepare(self.group, self.index, self.index_hash, self.finest, self.dev)
+    pos, fin, neg = self.crit.finest_contrastive_loss(F, None, None, None, None, max_pos_cluster=256 * self.samples,
+                                                      max_hn_samples=256 * self.samples, prepared=self.prepared)
     loss = pos + fin + neg
     loss.backward()
     self.grads.allreduce()            # the path's only exchange step (NCCL over NVLink when world > 1)
