@@ -239,7 +239,39 @@ def conv_roofline(matcher, xyz_dev, ptr, peaks):
       traffic_src = f"profiles/conv_traffic.json is stale (build {tj.get('build_id')} != {_b.source_id()}): not reported"
   except Exception:
     pass
-  return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+  # K1 (voxelise + hash) and K2 (strided maps + kernel maps + row bucketing) with SURVEY 8(d)'s byte formulas, CUDA events around
+  # each group of launches on the launching stream (GPU kept busy so that the events bracket execution, not launch latency)
+  def timed_ms(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    torch.cuda._sleep(int(2e7))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+  P = xyz_dev.shape[0]
+  k1_ms, (cm_k1, _) = timed_ms(lambda: ops.voxelize(xyz_dev, VOXEL, ptr))
+  k1_bytes = 12 * P + 16 * cm_k1.n + 8 * cm_k1.n
+  k2_ms, (cms2, km2) = timed_ms(lambda: eng.build_maps(ops.voxelize(xyz_dev, VOXEL, ptr)[0]))
+  k2_ms -= k1_ms                       # build_maps needs a fresh coordinate map each time; its cost is subtracted
+  n_of = {1: cms[1].n, 2: cms[2].n, 4: cms[4].n, 8: cms[8].n}
+  k2_bytes = sum(16 * n_of[s] + 16 * n_of[2 * s] for s in (1, 2, 4))                     # strided maps: 16 N_in + 16 N_out
+  geo = {"k3s1": (1, 1), "k3s2": (2, 2), "k3s4": (4, 4), "k3s8": (8, 8), "down1": (1, 2), "down2": (2, 4), "down4": (4, 8),
+         "up1": (2, 1), "up2": (4, 2), "up4": (8, 4)}
+  for name, (s_in, s_out) in geo.items():
+    if name in pair_counts and name != "k3s1":   # k3s1 is emitted by conv1's fused probe, not by a K2 launch
+      k2_bytes += 16 * n_of[s_out] + 8 * pair_counts[name] + 16 * n_of[s_in]
+  roof_k = {"roofline_k1": {"bound": "hbm", "kernel": "gclb_voxelize (insert_rows + count_winners + scan + scatter_winners)",
+                            "achieved": round(k1_bytes / (k1_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, 4), "ms_per_step": round(k1_ms, 3),
+                            "algorithmic_bytes_per_step": int(k1_bytes), "traffic": None},
+            "roofline_k2": {"bound": "hbm", "kernel": "strided maps + kernel maps (kmap_build[_up]) + row bucketing (rowkey_scatter, permute_rows)",
+                            "achieved": round(k2_bytes / (max(k2_ms, 1e-6) * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(k2_bytes / (max(k2_ms, 1e-6) * 1e-3) / 1e9 / peak, 4), "ms_per_step": round(k2_ms, 3),
+                            "algorithmic_bytes_per_step": int(k2_bytes), "traffic": None,
+                            "note": "SM-issue / L2-latency bound integer kernels (hash probes): far from the HBM roofline by nature"}}
+  return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), **roof_k,
           "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(tot_b / max(len(recs), 1)),
           "kernel": "spconv_fwd_tc_kernel (tcgen05 sparse conv, all 22 launches of a step incl. the 2 pointwise tail layers)", "launches": len(recs),
           "avg_launch_ms": round(tot_ms / len(recs), 4), "conv_ms_per_step": round(tot_ms, 3),
@@ -772,7 +804,8 @@ def main():
                          "unit": "pairs/s", "ms_per_step": round(ms_reg / reg_steps, 3), "steps": reg_steps,
                          "what": "same step + SC2-PCR registration of every pair on the GPU (5000 putative correspondences per pair, "
                                  "config_KITTI.json), 4x4 transforms read back"},
-          "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": [int(new_segments), int(new_segments_e2e)], "clocks": clk, "roofline": roof}
+          "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": [int(new_segments), int(new_segments_e2e)], "clocks": clk,
+          "roofline_k1": roof.pop("roofline_k1"), "roofline_k2": roof.pop("roofline_k2"), "roofline": roof}
   if world == 1 and not args.no_cpu_baseline:
     r = run_cpu(steps=5, warmup=1, n_pairs_per_step=1)
     line["cpu_baseline"] = {"value": round(r["pairs_per_s"], 4), "unit": "pairs/s", "cores": r["cores"], "kind": "port",

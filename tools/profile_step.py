@@ -20,18 +20,25 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--train", action="store_true")
   ap.add_argument("--pairs", type=int, default=16)
+  ap.add_argument("--register", action="store_true", help="also run SC2-PCR registration of every pair inside the profiled step")
   args = ap.parse_args()
   dev = torch.device("cuda:0")
-  if args.train:
-    sys.argv = [sys.argv[0], "--tf32", "--steps", "1"]
-    os.environ["GCLB_PROFILE_LAST_STEP"] = "1"
-    import runpy
-    runpy.run_path(os.path.join(ROOT, "tools", "bench_train.py"), run_name="__main__")
+  if args.train:     # one GCL training step (bench.py --workload train's step) inside the profiled range
+    from gcl_b200.training import GclTrainStep
+    ts = GclTrainStep(dev, samples=4)
+    for _ in range(6):
+      ts.step()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    ts.step()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     return
   import bench
   from gcl_b200 import MinkowskiEngine as ME
   from gcl_b200.pipeline import PairMatcher
-  matcher = PairMatcher(bench.seeded_model(ME), voxel=bench.VOXEL, subsample=bench.SUBSAMPLE, device=dev, seed=0)
+  matcher = PairMatcher(bench.seeded_model(ME), voxel=bench.VOXEL, subsample=bench.SUBSAMPLE, device=dev, seed=0,
+                        register=args.register)
   batches = [(x.to(dev), p) for x, p in bench.make_batches(2, args.pairs, seed=0)]
   for i in range(3):
     matcher.match(*batches[i % 2])
