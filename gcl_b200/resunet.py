@@ -4,7 +4,7 @@ The reference's model file (/root/reference/model/resunet.py:11-232, residual_bl
 runs unmodified on `gcl_b200.MinkowskiEngine`; this module exists because the reference tree is not present
 on the GPU box, and because the fused inference engine (gcl_b200/engine.py) needs the layer table.  It
 produces the *same module names and state_dict keys/shapes* as the reference classes (checkpoint contract,
-SURVEY.md Appendix A10), verified in tests/test_reference_model_on_oracle.py.
+SURVEY.md Appendix A10), verified in tests/test_reference_live.py (build container) and the golden tests/golden/resunet_bn2c.npz.
 
 `make_models(ME)` returns {'ResUNetBN2C': cls, ...} built on the given operator module, so the same graph
 is instantiated over the CUDA operators (product) or over the CPU oracle (tests).

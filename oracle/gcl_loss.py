@@ -8,8 +8,8 @@ and the pair-hash helpers /root/reference/util/misc.py:29-40 (_exhaustive_hash, 
 
 The host-side random selections (pos_sel :456-459, sel_hn1/sel_hn2 :506-507) are drawn from `rng` with the
 same calls in the same order as the reference, so a seeded run reproduces the reference's selection.
-Pinned against the reference functions imported in the build container (tests/test_oracle_vs_reference_py.py;
-golden vectors tests/golden/gcl_loss_*.npz).
+Pinned against the reference functions imported in the build container (tests/test_reference_live.py;
+golden vectors tests/golden/gcl_loss.npz, pair_hash.npz; tests/test_oracle_golden.py).
 """
 import numpy as np
 import torch

@@ -7,7 +7,7 @@ Restates, in torch-CPU / numpy:
   find_corr      /root/reference/scripts/test_kitti.py:29-43
   match_pair     /root/reference/scripts/SC2_PCR/SC2_PCR.py:276-302 (literal formula: sqrt(2 - 2 F0 F1^T + 1e-6), argmin)
 Pinned against the reference's own functions imported in the build container
-(tests/test_oracle_vs_reference_py.py; golden vectors tests/golden/nn_*.npz, generator tests/golden/make_golden.py).
+(tests/test_reference_live.py; golden vectors tests/golden/nn.npz, tests/test_oracle_golden.py, generator tests/golden/make_golden.py).
 """
 import numpy as np
 import torch

@@ -8,7 +8,7 @@ which ships no golden vectors.  This module restates ME 0.5.x's *documented* ope
   (1) independent known-answer tests against dense `torch.nn.functional.conv3d` / `conv_transpose3d`
       (tests/test_oracle_dense_equiv.py), and
   (2) the reference's own call sites: `/root/reference/model/resunet.py` imports and runs unmodified on
-      top of this module (tests/test_reference_model_on_oracle.py; fixtures in tests/golden/).
+      top of this module (tests/test_reference_live.py; fixtures in tests/golden/).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may
 import this package.  The product (`gcl_b200`) never does.
