@@ -30,3 +30,27 @@ def test_non_zero_rank_of_the_reference_arm_exits_quietly():
   r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                       "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
   assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_training_workload_reference_arm_and_batch_generator():
+  """BASELINE config 4: the oracle arm of `bench.py --workload train` runs on the CPU and prints the contract line; the synthetic
+  colocated-scan batch (host side of gcl_b200.training) yields voxel-downsampled clouds with valid neighbour poses"""
+  import numpy as np
+  sys.path.insert(0, ROOT)
+  from gcl_b200.training import synthetic_group_batch
+  batch = synthetic_group_batch(rank=0, samples=1, voxel=0.3)
+  assert len(batch) == 1
+  clouds, Ts = batch[0]
+  assert len(clouds) == 3 and len(Ts) == 2
+  for c in clouds:
+    assert c.dtype == np.float32 and c.shape[1] == 3 and len(c) > 1000
+    key = np.floor(c / 0.3).astype(np.int64)
+    assert len(np.unique(key, axis=0)) == len(c)                 # one point per voxel, like the loader's voxel_down_sample
+  for T in Ts:
+    assert T.shape == (4, 4) and abs(np.linalg.det(T[:3, :3]) - 1) < 1e-9
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "train", "--impl", "reference", "--steps", "1",
+                      "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+  assert r.returncode == 0, r.stderr[-2000:]
+  d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+  assert d["impl"] == "reference" and d["metric"] == "gcl_train_scans_per_sec" and d["unit"] == "scans/s" and d["value"] > 0
+  assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
