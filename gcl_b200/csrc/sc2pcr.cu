@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(128) sc_seed_hyp_kernel(ScParams p) {
   for (int q = 0; q < 3; ++q) tf[q] = __shfl_sync(0xffffffffu, tf[q], 0);
   // inlier count of the hypothesis over all correspondences (:146-157)
   int cnt = 0;
-  for (int j = lane; j < n; j += 32) {
+#pragma unroll 4
+  for (int j = lane; j < n; j += 32) {      // unrolled: four independent load pairs in flight per lane (the loop is latency-bound)
     const float4 x = __ldg(S + j), y = __ldg(T + j);
     const float px = Rf[0] * x.x + Rf[1] * x.y + Rf[2] * x.z + tf[0] - y.x;
     const float py = Rf[3] * x.x + Rf[4] * x.y + Rf[5] * x.z + tf[1] - y.y;
