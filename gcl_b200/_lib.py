@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libgclb200.so")
 
 _p, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
-# name -> (restype, argtypes): must list every symbol of include/gclb200.h (tests/test_abi.py checks it)
+# name -> (restype, argtypes): must list every symbol of include/gclb200.h and include/gclb200_debug.h (tests/test_abi.py checks it)
 SIGNATURES = {
     "gclb_last_error": (C.c_char_p, []),
     "gclb_version": (C.c_int, []),
@@ -53,7 +53,6 @@ SIGNATURES = {
     "gclb_spconv_wgrad_tc": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _p, _i32, _p, _p]),
     "gclb_pointwise_tail": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _p, _i32, _i32, _p, _p]),
     "gclb_affine_act": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
-    "gclb_bn_stats": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "gclb_bn_train_fwd": (C.c_int, [_p, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "gclb_bn_train_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "gclb_nn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i64, _i64]),

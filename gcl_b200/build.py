@@ -25,7 +25,8 @@ def source_id() -> str:
   import hashlib
   h = hashlib.sha1()
   files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
-  for f in files + [os.path.join(os.path.dirname(HERE), "include", "gclb200.h")]:
+  inc = os.path.join(os.path.dirname(HERE), "include")
+  for f in files + [os.path.join(inc, h) for h in sorted(os.listdir(inc)) if h.endswith(".h")]:
     with open(f if os.path.isabs(f) else os.path.join(CSRC, f), "rb") as fh:
       h.update(fh.read())
   return h.hexdigest()[:12]
@@ -45,7 +46,8 @@ def _newer(target, deps):
 def build(force: bool = False, verbose: bool = False) -> str:
   os.makedirs(OBJ, exist_ok=True)
   headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-  headers.append(os.path.join(os.path.dirname(HERE), "include", "gclb200.h"))
+  inc = os.path.join(os.path.dirname(HERE), "include")
+  headers += [os.path.join(inc, h) for h in os.listdir(inc) if h.endswith(".h")]
   jobs = []
   for s in sources():
     src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")

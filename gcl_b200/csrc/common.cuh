@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "../../include/gclb200.h"
+#include "../../include/gclb200_debug.h"
 
 namespace gclb {
 

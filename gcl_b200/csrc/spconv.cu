@@ -470,25 +470,6 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
   }
 }
 
-// per-channel sum / sum of squares over rows (training-mode BatchNorm): block partials in fp32 over <= 64 rows,
-// merged into fp64 accumulators.
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* sum,
-                                                       double* sumsq) {
-  const int rows_per_block = 256;
-  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t r1 = min(n, r0 + rows_per_block);
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int64_t r = r0; r < r1; ++r) {
-      float v = x[r * c + ch];
-      s += v;
-      q += (double)v * v;
-    }
-    atomicAdd(&sum[ch], s);
-    atomicAdd(&sumsq[ch], q);
-  }
-}
-
 static thread_local uint32_t* g_range_mon = nullptr;
 uint32_t* current_range_monitor() { return g_range_mon; }
 
@@ -649,15 +630,6 @@ int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, co
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
   affine_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, total, c, scale, shift, residual, relu, y);
-  count_launches(1);
-  GCLB_CHECK_LAUNCH();
-  return GCLB_OK;
-}
-
-int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sumsq, void* stream) {
-  GCLB_CHECK_ARG(c >= 1 && sum && sumsq && (n == 0 || x), "bad arguments");
-  if (n == 0) return GCLB_OK;
-  bn_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, sum, sumsq);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

@@ -221,10 +221,6 @@ int gclb_spconv_fwd_probe(const float* in, int32_t cin, const float* W, int32_t 
  * gclb_spconv_fwd_halo: arguments as gclb_spconv_fwd (K = 27; flags bit 3 required; bits 0, 1, 4, 5 as there); W is the
  *   fp16 image from gclb_weights_to_tc_f16 with the matching slab width. */
 size_t gclb_kmap_halo_bytes(int64_t n_out);
-/* bring-up helper: per-CTA cycle accounting of the last gclb_spconv_fwd_halo launch run with GCLB_HALO_DBG bit 9 (host uint64 [148][16]) */
-int gclb_debug_halo_prof(unsigned long long* out_host);
-/* bring-up helper: tcgen05.mma issue / completion cycles (M = 128, N = n, K = 16, kind::f16), out_dev int64[2] */
-int gclb_debug_umma_rate(int32_t n, int32_t n_mma, int32_t per_commit, int32_t n_acc, int32_t elect, long long* out_dev, void* stream);
 int32_t gclb_kmap_halo_max_groups(void);
 int gclb_kmap_halo_build(const int32_t* nbr, int64_t n_out, const int32_t* row_perm, void* records, size_t record_bytes,
                          int32_t* tile_groups, int32_t* tile_ngroups, uint64_t* counter, int32_t* status, void* stream);
@@ -254,8 +250,6 @@ int gclb_pointwise_tail(const float* in0, int32_t c0, const float* in1, int32_t 
 /* elementwise helpers for the op-by-op (training) path: y = act(x * scale[c] + shift[c] + residual) */
 int gclb_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
                     const float* residual, int32_t relu, float* y, void* stream);
-/* training-mode BatchNorm statistics over all rows: sum[c], sumsq[c] as float64 (caller-zeroed) */
-int gclb_bn_stats(const float* x, int64_t n, int32_t c, double* sum, double* sumsq, void* stream);
 /* MinkowskiBatchNorm in TRAINING mode (model/common.py:6 = torch.nn.BatchNorm1d over the rows of .F; forward
  * lib/colocation_trainer.py:846, backward via loss.backward() :879), optionally fused with the MEF.relu that follows it in
  * every residual block (model/residual_block.py:42; model/resunet.py:177-223).
@@ -339,10 +333,6 @@ int gclb_group_loss_bwd(const float* F, int64_t N, int32_t C, const int64_t* gro
                         float pos_thresh, float finest_thresh, float neg_thresh, int32_t square_loss,
                         const float* upstream, float* losses_scratch, float* gradF, void* workspace, void* stream);
 
-/* bring-up helper (not on the hot path): one TMA tile::gather4 of rows rows4_host[0..3] x channels [col, col+32) of the
- * fp32 matrix X [n, c] into a SWIZZLE_128B shared-memory tile, dumped to out256 (device, 256 floats). */
-int gclb_debug_tma_gather4(const float* X, int64_t n, int32_t c, int32_t box_rows, int32_t col, const int32_t* rows4_host,
-                           float* out256, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Data ingest: velodyne records -> the point matrix K1 voxelises.

@@ -7,13 +7,17 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADERS = [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h")]
 HEADER = os.path.join(ROOT, "include", "gclb200.h")
 
 
 def _declared():
-  src = open(HEADER).read()
-  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-  return sorted(set(re.findall(r"\b(gclb_[a-z0-9_]+)\s*\(", src)))
+  names = set()
+  for h in HEADERS:
+    src = open(h).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names |= set(re.findall(r"\b(gclb_[a-z0-9_]+)\s*\(", src))
+  return sorted(names)
 
 
 @pytest.fixture(scope="module")
