@@ -745,11 +745,19 @@ def main():
       ingest.write_velodyne_bin(fn, x[pl[c]:pl[c + 1]].numpy())
       paths.append(fn)
     file_batches.append(paths)
-  readers = [ingest.ScanReader(capacity_points=max(x.shape[0] for x, _ in host) + 1024) for _ in range(max(args.depth, 1) + 1)]
+  readers = [ingest.ScanReader(capacity_points=max(x.shape[0] for x, _ in host) + 1024, threads=min(16, os.cpu_count() or 1))
+             for _ in range(max(args.depth, 1) + 2)]
+  import concurrent.futures as cf
+  prefetch = cf.ThreadPoolExecutor(max_workers=1)
 
   def disk_source(n):
+    # the next batch's files are read (into their own pinned buffer) by a background thread while this thread enqueues the
+    # current batch; file reads release the GIL
+    nxt = prefetch.submit(readers[0].read, file_batches[0]) if n else None
     for i in range(n):
-      rec, ptr = readers[i % len(readers)].read(file_batches[i % n_batches])
+      rec, ptr = nxt.result()
+      if i + 1 < n:
+        nxt = prefetch.submit(readers[(i + 1) % len(readers)].read, file_batches[(i + 1) % n_batches])
       yield ingest.points_to_device(rec, ptr, dev), ptr
 
   def run_disk(steps):
@@ -774,6 +782,7 @@ def main():
   if world > 1:
     t = torch.tensor([ms_disk], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_disk = t.item()
   import shutil
+  prefetch.shutdown(wait=True)
   shutil.rmtree(tmpdir, ignore_errors=True)
 
   total_pairs = args.pairs * args.steps * world
