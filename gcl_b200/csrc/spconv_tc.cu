@@ -11,7 +11,8 @@
 //               canonical K-major SWIZZLE_128B layout -- the TMA swizzles and zero-fills missing neighbours (index -1 is
 //               out of bounds); lane 0 also pulls the weight slab with ONE cp.async.bulk (weights are stored
 //               pre-swizzled, see gclb_weights_to_tc) onto the same mbarrier.  No LSU traffic, no thread waits for data.
-//   warp  8     one elected thread issues tcgen05.mma; tcgen05.commit recycles smem slots and publishes accumulators.
+//   warp  8     issues tcgen05.mma from one elected lane of a warp-uniform loop (descriptors stay in uniform registers);
+//               tcgen05.commit recycles smem slots and publishes accumulators.
 //   warp  9     prefetches the next tile's slice of the neighbour table (cp.async) and lists its populated offsets.
 //   warps 10-13 epilogue: tcgen05.ld (thread <-> output row), fused scale/shift (+residual) (+ReLU) (+L2 normalise),
 //               overlapped with the next tile's main loop through a double-buffered TMEM accumulator.
@@ -64,10 +65,11 @@ struct TcShared {   // static shared: barriers + small per-tile metadata
   int n_act[4];
   int acc_n_act[4];        // per accumulator: number of populated offsets of the tile it holds (0 => treat as zeros)
   int act_k[4][32];
+  uint4 lane_mask[8];      // per ring slot: rows (TMEM lanes) whose neighbour is missing at this stage's offset => MMA output switched off
 };
 
 template <int COUT, int KVOL, int MODE, int CTAS>
-__global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize,
+__global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_kernel(ConvParams p, int num_tiles, int normalize, int dbg,
                                                                       const __grid_constant__ CUtensorMap map0,
                                                                       const __grid_constant__ CUtensorMap map1) {
   using Cfg = TcCfg<COUT, MODE, CTAS>;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
   unsigned char* ring = smem_dyn;
   int* nbr_buf = reinterpret_cast<int*>(smem_dyn + S * Cfg::STAGE);    // [NBUF][NBR_INTS]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)warp_uniform((uint32_t)(threadIdx.x >> 5)), lane = tid & 31;   // role index: provably warp-uniform
   // HALF: activations (in0, in1, residual) are IEEE fp16 in HBM, weights an fp16 image, MMA kind::f16 -- a 128-byte
   // operand row then holds 64 channels instead of 32: half the gather bytes, same 10-bit mantissa as kind::tf32
   constexpr int KCH = MODE == 1 ? 64 : 32;
@@ -114,6 +116,14 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
   tc_fence_after();
   const uint32_t tmem_base = sh.tmem_base;
   const uint32_t ring_u32 = smem_u32(ring);
+  // the row-masked MMAs only ever accumulate: every accumulator starts (and is handed back by the epilogue) as zeros
+  if (warp >= TcRoles<CTAS>::kEpiWarp0) {
+    for (int c0 = 0; c0 < Cfg::TMEM_COLS; c0 += 32) tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < kGatherWarps) {
     if (warp < S) {
@@ -138,15 +148,38 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
         const int stage = it % S;
         int r[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) r[q] = identity ? (tile_m + 4 * lane + q) : nb[(4 * lane + q) * KVOL + k];
+        for (int q = 0; q < 4; ++q) {
+          if (identity) { const int64_t t_row = (int64_t)tile_m + 4 * lane + q; r[q] = t_row < p.n_out ? (int)t_row : -1; }
+          else r[q] = nb[(4 * lane + q) * KVOL + k];
+        }
+        // Missing neighbours are NOT fetched: an out-of-bounds row of a gather4 is zero-filled correctly but costs ~4x an
+        // in-bounds row (measured, profiles/r02_conv_ablation.md).  Instead the MMAs of this stage run with those rows'
+        // output lanes switched off.  A quad with no valid row issues nothing; inside a partly valid quad the missing slots
+        // re-fetch a valid row of the same quad (same line, L2-hot; its product is masked out).
+        const uint32_t nib = (uint32_t)(r[0] >= 0) | ((uint32_t)(r[1] >= 0) << 1) | ((uint32_t)(r[2] >= 0) << 2) | ((uint32_t)(r[3] >= 0) << 3);
+        const int fv = (nib & 1u) ? r[0] : (nib & 2u) ? r[1] : (nib & 4u) ? r[2] : r[3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = r[q] >= 0 ? r[q] : fv;
+        const uint32_t quads = __ballot_sync(0xffffffffu, nib != 0u);
+        const uint32_t off_bits = (nib ^ 15u) << (4 * (lane & 7));      // smem row 4*lane + q <-> TMEM lane 4*lane + q
+        uint4 dm;
+        dm.x = __reduce_or_sync(0xffffffffu, (lane >> 3) == 0 ? off_bits : 0u);
+        dm.y = __reduce_or_sync(0xffffffffu, (lane >> 3) == 1 ? off_bits : 0u);
+        dm.z = __reduce_or_sync(0xffffffffu, (lane >> 3) == 2 ? off_bits : 0u);
+        dm.w = __reduce_or_sync(0xffffffffu, (lane >> 3) == 3 ? off_bits : 0u);
         mbar_wait(&sh.empty[stage], ((it / S) & 1u) ^ 1u);   // passes immediately during the first round
         const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
         if (lane == 0) {
-          mbar_arrive_expect_tx(&sh.full[stage], A_BYTES + Cfg::B_BYTES);
-          bulk_g2s(a_s + A_BYTES, reinterpret_cast<const unsigned char*>(p.W) + ((size_t)k * slabs + c / KCH) * Cfg::B_BYTES,
-                   Cfg::B_BYTES, &sh.full[stage]);
+          sh.lane_mask[stage] = dm;                          // published by the arrive below (release) to the MMA warp
+          const uint32_t bytes = ((dbg & 1) ? 0u : (uint32_t)__popc(quads) * (4u * ROWB)) + ((dbg & 2) ? 0u : (uint32_t)Cfg::B_BYTES);   // ablation: GCLB_TC_DBG
+          if (bytes) mbar_arrive_expect_tx(&sh.full[stage], bytes);
+          else mbar_arrive(&sh.full[stage]);
+          if (!(dbg & 2))
+            bulk_g2s(a_s + A_BYTES, reinterpret_cast<const unsigned char*>(p.W) + ((size_t)k * slabs + c / KCH) * Cfg::B_BYTES,
+                     Cfg::B_BYTES, &sh.full[stage]);
         }
         __syncwarp();                                        // the barrier is armed before any gather can complete on it
+        if ((dbg & 1) || nib == 0u) continue;
         if (c < p.c0) tma_gather4(a_s + lane * (4 * ROWB), &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
         else tma_gather4(a_s + lane * (4 * ROWB), &map1, &sh.full[stage], c - p.c0, r[0], r[1], r[2], r[3]);
       }
@@ -155,43 +188,54 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
     }
     }
   } else if (warp == kMmaWarp) {
-    // ======================================= MMA issuer (one thread) =======================================
-    if (lane == 0) {
+    // ======================================= MMA issuer (warp-uniform loop, one elected lane) ================
+    // The whole warp walks the tile / stage loop on warp-uniform values; only the tcgen05 instructions and the barrier
+    // arrivals sit under elect.sync.  That keeps the descriptors in uniform registers (see tc_common.cuh: 59 instead of
+    // 110 cycles per tcgen05.mma at N = 64 -- this thread's issue chain bounds the kernel, profiles/r02_conv_ablation.md).
+    {
       constexpr uint32_t idesc = HALF ? make_idesc_f16(COUT) : make_idesc_tf32(COUT);
-      uint32_t it = 0;
+      constexpr uint32_t HI = MODE == 2 ? kDescHiSw64 : kDescHiSw128;
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const uint32_t ring_lo = desc_lo(ring_u32);
+      uint32_t stage = 0, phase = 0;       // ring position of the global stage counter (identical in every role)
       int lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = lt % NBUF, ab = lt % NACC;
         mbar_wait(&sh.nbr_full[b], (lt / NBUF) & 1);
-        const int n_act = sh.n_act[b];
+        const int n_act = (int)warp_uniform((uint32_t)sh.n_act[b]);      // every lane has read it before the arrive below
         const int n_iter = n_act * slabs;
-        mbar_arrive(&sh.nbr_empty[b]);
+        if (elect_one()) mbar_arrive(&sh.nbr_empty[b]);
         mbar_wait(&sh.acc_empty[ab], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        *reinterpret_cast<volatile int*>(&sh.acc_n_act[ab]) = n_act;   // read by the epilogue after acc_full
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * COUT);
-        for (int i = 0; i < n_iter; ++i, ++it) {
-          const int stage = it % S;
-          mbar_wait(&sh.full[stage], (it / S) & 1u);
+        if (elect_one()) *reinterpret_cast<volatile int*>(&sh.acc_n_act[ab]) = n_act;   // read by the epilogue after acc_full
+        const uint32_t d_tmem = tmem_u + (uint32_t)(ab * COUT);
+        for (int i = 0; i < n_iter; ++i) {
+          mbar_wait(&sh.full[stage], phase);
           tc_fence_after();
-          const uint32_t a_s = ring_u32 + stage * Cfg::STAGE;
-          const uint32_t b_s = a_s + A_BYTES;
-          if constexpr (HALF) {   // lean issue path (tc_common.cuh): the issuing thread, not the tensor pipe, bounds N <= 128
-            constexpr uint32_t HI = MODE == 2 ? kDescHiSw64 : kDescHiSw128;
-            const uint32_t a_lo = desc_lo(a_s), b_lo = desc_lo(b_s);
-            if (i == 0) umma_f16_lo<HI, false>(d_tmem, a_lo, b_lo, idesc);
-            else umma_f16_lo<HI, true>(d_tmem, a_lo, b_lo, idesc);
+          const uint32_t a_lo = ring_lo + stage * (uint32_t)(Cfg::STAGE >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(A_BYTES >> 4);
+          uint4 dmv;                                   // ordered after the barrier's acquire by the asm's memory clobber
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dmv.x), "=r"(dmv.y), "=r"(dmv.z), "=r"(dmv.w) : "r"(smem_u32(&sh.lane_mask[stage])) : "memory");
+          const uint32_t m0 = warp_uniform(dmv.x), m1 = warp_uniform(dmv.y), m2 = warp_uniform(dmv.z), m3 = warp_uniform(dmv.w);
+          if (elect_one()) {
+            if (dbg & 4) {   // ablation: no MMAs (the commits still recycle the ring)
+            } else if constexpr (HALF) {
 #pragma unroll
-            for (int ks = 1; ks < ROWB / 32; ++ks) umma_f16_lo<HI, true>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc);
-          } else {
+              for (int ks = 0; ks < ROWB / 32; ++ks) umma_f16_um<HI>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, m0, m1, m2, m3);
+            } else {
 #pragma unroll
-            for (int ks = 0; ks < ROWB / 32; ++ks)   // MMAs of 32 bytes of K (8 tf32) inside the swizzle row
-              umma_tf32(d_tmem, make_desc_sw128(a_s + ks * 32), make_desc_sw128(b_s + ks * 32), idesc, (i | ks) ? 1u : 0u);
+              for (int ks = 0; ks < ROWB / 32; ++ks) umma_tf32_um<HI>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, m0, m1, m2, m3);
+            }
+            umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
           }
-          umma_commit(&sh.empty[stage]);            // frees the slot once these MMAs have read it
+          __syncwarp();
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
-        if (n_iter > 0) umma_commit(&sh.acc_full[ab]);
-        else mbar_arrive(&sh.acc_full[ab]);
+        if (elect_one()) {
+          if (n_iter > 0) umma_commit(&sh.acc_full[ab]);
+          else mbar_arrive(&sh.acc_full[ab]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == kNbrWarp) {
@@ -258,11 +302,17 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
     // ======================================= epilogue: thread <-> output row ================================
     const int quarter = warp & 3;                      // TMEM lanes this warp may read
     uint32_t amax_bits = 0u;                           // fp16-range monitor: max |y| (float bits; NaN sorts above inf)
+    // row ids two tiles ahead, first residual chunk one tile ahead (tc_epilogue.cuh: the epilogue is a per-tile serial chain)
+    EpiState<HALF> est;
+    est.o_cur = epi_row_id(p, blockIdx.x, quarter * 32 + lane, num_tiles);
+    est.o_next = epi_row_id(p, (int64_t)blockIdx.x + gridDim.x, quarter * 32 + lane, num_tiles);
+    epi_residual_first<COUT, HALF>(p, est.o_cur, est.rc);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt % NACC;
-      tc_epilogue_tile<COUT, HALF>(p, tile, quarter, lane, normalize, &sh.acc_full[ab], (lt / NACC) & 1, &sh.acc_empty[ab],
-                                   &sh.acc_n_act[ab], tmem_base + (uint32_t)(ab * COUT), amax_bits);
+      tc_epilogue_tile<COUT, HALF, false, true, true>(p, tile, quarter, lane, normalize, &sh.acc_full[ab], (lt / NACC) & 1,
+                                                      &sh.acc_empty[ab], &sh.acc_n_act[ab], tmem_base + (uint32_t)(ab * COUT),
+                                                      amax_bits, dbg, &est, tile + 2 * (int)gridDim.x, num_tiles);
     }
     if (p.range_mon) range_mon_flush(p.range_mon, amax_bits);   // saturation / NaN / tiny tensors are reported, never silent
   }
@@ -330,7 +380,10 @@ static int launch_tc_n(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   int rc = make_rows_tensor_map_ex(&map0, p.in0, n_in, p.c0, MODE, false);
   if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, MODE, false) : (map1 = map0, GCLB_OK);
   if (rc != GCLB_OK) return rc;
-  kern<<<grid, TcRoles<CTAS>::kThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, map0, map1);
+  // ablation switches for tools/tileprof.py (WRONG results on purpose): 1 no activation gathers, 2 no weight slabs, 4 no MMAs,
+  // 16 no epilogue math / stores
+  static const int dbg = getenv("GCLB_TC_DBG") ? atoi(getenv("GCLB_TC_DBG")) : 0;
+  kern<<<grid, TcRoles<CTAS>::kThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, dbg, map0, map1);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("spconv_fwd_tc: CUDA error: %s", cudaGetErrorString(e));

@@ -124,6 +124,77 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
         : "memory");
   }
 }
+// Warp-uniform issue path.  tcgen05.mma takes its descriptors from UNIFORM registers.  Issued from `if (lane == 0)` -- a
+// divergent region -- every instruction is preceded by R2UR moves into the same uniform registers, which have to wait until
+// the previous tcgen05.mma has read them: measured 95 cycles per instruction (110 with a commit per four), whatever N.  When
+// the whole warp runs the issue loop on warp-uniform values and only the tcgen05 instructions sit under elect.sync, the
+// compiler keeps the descriptors in uniform registers and emits the MMAs back to back: 56 / 59 / 64 cycles per instruction at
+// N = 32 / 64 / 128 (the last one is the tensor pipe's own floor), commits free (tools/umma_rate.py, profiles/r02_conv_ablation.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+template <uint32_t HI>
+__device__ __forceinline__ void umma_f16_u(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+template <uint32_t HI>
+__device__ __forceinline__ void umma_tf32_u(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Row-masked accumulate: `tcgen05.mma` with a disable-output-lane vector (bit i of word j set => TMEM lane 32 j + i, i.e. row
+// 32 j + i of D, is NOT updated).  The sparse convolution uses it for missing neighbours: the operand row of a missing
+// neighbour is never fetched (no zero fill, shared memory holds whatever was there) and its output row is switched off for the
+// MMAs of that kernel offset.  Always accumulates: the accumulator is zeroed by the epilogue (tcgen05.st) when it is drained.
+template <uint32_t HI>
+__device__ __forceinline__ void umma_f16_um(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t m0,
+                                            uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(HI), "r"(idesc), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+template <uint32_t HI>
+__device__ __forceinline__ void umma_tf32_um(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t m0,
+                                             uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(HI), "r"(idesc), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+// 32 lanes x 32 columns of zeros into TMEM (thread <-> lane), and the matching wait
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -11,26 +11,65 @@ namespace gclb {
 // tmem_acc: TMEM address of the accumulator (lane 0, first column); amax_bits: running fp16-range monitor (common.cuh)
 // DUAL: two MMA issuers accumulated alternate pipeline stages into two accumulators (tmem_acc and tmem_acc + COUT; acc_n_act
 // is int[2]: stages each one issued, 0 => that accumulator holds stale data); the epilogue adds them in a fixed order.
-template <int COUT, bool HALF, bool DUAL = false>
+// ZERO: the accumulator is handed back ZEROED (tcgen05.st after every chunk is read): the direct kernel's row-masked MMAs
+// always accumulate and never touch the rows whose neighbour is missing.
+// PIPE: the four epilogue warps drain ONE tile at a time, so whatever latency a tile's epilogue exposes is paid once per tile
+// by the whole CTA.  Fetching the output row id (perm) and then the residual row (address depends on it) inside the tile's own
+// epilogue is two dependent L2/DRAM round trips = 2-3 us per tile -- more than the tile's MMAs.  With PIPE the caller keeps an
+// EpiState across tiles: row ids are fetched two tiles ahead, the first residual chunk one tile ahead.
+template <bool HALF>
+struct EpiState {
+  static constexpr int RV = HALF ? 4 : 8;   // 16-byte vectors per 32 residual columns
+  int64_t o_cur, o_next;                    // output row of this thread in the current / next tile (n_out = none)
+  float4 rc[RV];                            // first 32 residual columns of the current tile
+};
+__device__ __forceinline__ int64_t epi_row_id(const ConvParams& p, int64_t tile, int row, int num_tiles) {
+  const int64_t t_row = tile * TM + row;
+  if (tile >= num_tiles || t_row >= p.n_out) return p.n_out;
+  return p.perm ? (int64_t)__ldg(p.perm + t_row) : t_row;
+}
+template <int COUT, bool HALF>
+__device__ __forceinline__ void epi_residual_first(const ConvParams& p, int64_t o, float4* rc) {
+  constexpr int RV = HALF ? 4 : 8;
+  const bool have = p.residual && o < p.n_out;
+  const float4* res = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.residual) + (size_t)o * COUT * (HALF ? 2 : 4));
+#pragma unroll
+  for (int q = 0; q < RV; ++q) rc[q] = have ? __ldg(res + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int COUT, bool HALF, bool DUAL = false, bool ZERO = false, bool PIPE = false>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, int quarter, int lane, int normalize,
                                                  uint64_t* acc_full, uint32_t acc_parity, uint64_t* acc_empty,
-                                                 const int* acc_n_act, uint32_t tmem_acc, uint32_t& amax_bits, int dbg = 0) {
+                                                 const int* acc_n_act, uint32_t tmem_acc, uint32_t& amax_bits, int dbg = 0,
+                                                 EpiState<HALF>* st = nullptr, int tile_next2 = 0, int num_tiles = 0) {
   const int row = quarter * 32 + lane;
   // everything that does not depend on the accumulator is fetched BEFORE waiting for it: the output row id and
   // the first 32 residual values, so their DRAM latency overlaps the tile's main loop
   const int64_t t_row = (int64_t)tile * TM + row;
   int64_t o = p.n_out;                                   // rows past the end are never stored
-  if (t_row < p.n_out) o = p.perm ? (int64_t)__ldg(p.perm + t_row) : t_row;
-  const bool live = o < p.n_out;
   // residual has the dtype of the inputs (it IS a block's input): 32 columns = 8 (fp32) or 4 (fp16) 16-byte loads
   constexpr int RV = HALF ? 4 : 8;
   constexpr int RES_B = HALF ? 2 : 4;
+  float4 rc[RV];
+  int64_t o_next2 = 0;
+  float4 rc_next[RV];
+  if constexpr (PIPE) {
+    o = st->o_cur;
+#pragma unroll
+    for (int q = 0; q < RV; ++q) rc[q] = st->rc[q];
+    o_next2 = epi_row_id(p, tile_next2, row, num_tiles);          // consumed two tiles from now
+    epi_residual_first<COUT, HALF>(p, st->o_next, rc_next);      // its row id was requested a whole tile ago
+  } else {
+    if (t_row < p.n_out) o = p.perm ? (int64_t)__ldg(p.perm + t_row) : t_row;
+  }
+  const bool live = o < p.n_out;
   const unsigned char* res = (p.residual && live) ? reinterpret_cast<const unsigned char*>(p.residual) + (size_t)o * COUT * RES_B
                                                    : nullptr;
   const bool out_half = (p.relu & 16) != 0;
-  float4 rc[RV];
+  if constexpr (!PIPE) {
 #pragma unroll
-  for (int q = 0; q < RV; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < RV; ++q) rc[q] = res ? __ldg(reinterpret_cast<const float4*>(res) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
   const bool has0 = *reinterpret_cast<const volatile int*>(acc_n_act) != 0;
@@ -54,7 +93,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, 
     for (int q = 0; q < RV; ++q)
       rn[q] = (more && res) ? __ldg(reinterpret_cast<const float4*>(res + (size_t)(n0 + 32) * RES_B) + q)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (ZERO) tmem_st32_zero(t_addr + (uint32_t)n0);
     if (!more) {                                        // last TMEM read of this tile: hand the accumulator back
+      if constexpr (ZERO) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
@@ -116,6 +157,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, 
     }
 #pragma unroll
     for (int q = 0; q < RV; ++q) rc[q] = rn[q];
+  }
+  if constexpr (PIPE) {
+    st->o_cur = st->o_next;
+    st->o_next = o_next2;
+#pragma unroll
+    for (int q = 0; q < RV; ++q) st->rc[q] = rc_next[q];
   }
 }
 

@@ -143,6 +143,63 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int n_mma, int per_commi
   __syncthreads();
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
+
+// the same measurement with a WARP-UNIFORM issue loop: all 32 lanes of the issuing warp run the loop, descriptors are
+// warp-uniform values, and only the tcgen05 instructions sit under elect.sync -- the compiler can then keep the descriptors
+// in uniform registers instead of moving them there (R2UR) once per instruction from a divergent thread
+template <int N>
+__global__ void __launch_bounds__(128) umma_rate_uniform_kernel(int n_mma, int per_commit, int n_acc, int elect, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_base;
+  for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { for (int q = 0; q < 4; ++q) mbar_init(&bars[q], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int n_issuers = elect < 1 ? 1 : elect;
+  const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  uint64_t& bar = bars[wid];
+  if (wid < n_issuers) {
+    const uint32_t tb = tmem_base + (uint32_t)(wid * N * n_acc);
+    const uint32_t a_s = smem_u32(smem), b_s = a_s + 16384;
+    constexpr uint32_t idesc = make_idesc_f16(N);
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    long long t_issue = 0;
+    const uint32_t a_lo = desc_lo(a_s), b_lo = desc_lo(b_s);
+    const int groups = n_mma / 4;
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t d = tb + (uint32_t)((g & (n_acc - 1)) * N);
+      if (elect_one()) {
+        umma_f16_lo<kDescHiSw128, true>(d, a_lo, b_lo, idesc);
+        umma_f16_lo<kDescHiSw128, true>(d, a_lo + 2, b_lo + 2, idesc);
+        umma_f16_lo<kDescHiSw128, true>(d, a_lo + 4, b_lo + 4, idesc);
+        umma_f16_lo<kDescHiSw128, true>(d, a_lo + 6, b_lo + 6, idesc);
+        if (per_commit >= 1) umma_commit(&bar);
+      }
+      __syncwarp();
+      if (per_commit == 2) { mbar_wait(&bar, phase); phase ^= 1; }
+    }
+    if (per_commit == 1) phase = (uint32_t)(groups & 1);
+    t_issue = clock64() - t0;
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, phase);
+    if ((threadIdx.x & 31) == 0) {
+      out[2 * wid] = clock64() - t0;
+      out[2 * wid + 1] = t_issue;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
 }  // namespace gclb
 
 extern "C" int gclb_debug_umma_rate(int32_t n, int32_t n_mma, int32_t per_commit, int32_t n_acc, int32_t elect, long long* out_dev, void* stream) {
@@ -152,7 +209,13 @@ extern "C" int gclb_debug_umma_rate(int32_t n, int32_t n_mma, int32_t per_commit
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, per_commit, n_acc, elect, out_dev);
   };
-  if (n == 32) go(gclb::umma_rate_kernel<32>);
+  if (per_commit >= 16) {   // bit 4: the warp-uniform issue loop (elect.sync), low bits as before
+    per_commit -= 16;
+    if (n == 32) go(gclb::umma_rate_uniform_kernel<32>);
+    else if (n == 64) go(gclb::umma_rate_uniform_kernel<64>);
+    else if (n == 128) go(gclb::umma_rate_uniform_kernel<128>);
+    else go(gclb::umma_rate_uniform_kernel<256>);
+  } else if (n == 32) go(gclb::umma_rate_kernel<32>);
   else if (n == 64) go(gclb::umma_rate_kernel<64>);
   else if (n == 128) go(gclb::umma_rate_kernel<128>);
   else go(gclb::umma_rate_kernel<256>);

@@ -3,10 +3,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gcl_b200 import _lib
 lib = _lib.load()
 out = torch.zeros(8, dtype=torch.int64, device="cuda")
-for n in (32, 64, 128):
+for n in (32, 64, 128, 256):
   for issuers in (1, 2, 4):
     if issuers * n > 512: continue
-    for per in (0, 1):
+    for per in (0, 1, 16, 17, 18):   # +16: warp-uniform issue loop under elect.sync; 2/18: commit + wait per 4 MMAs
       for _ in range(2):
         out.zero_()
         _lib.call("gclb_debug_umma_rate", n, 4000, per, 1, issuers, out.data_ptr(), None)
