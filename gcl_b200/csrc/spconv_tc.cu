@@ -6,16 +6,18 @@
 //   channels (2 per stage) for tensors whose width is a multiple of 32 only; see the operand modes below
 //
 // Persistent, warp-specialised CTA (one per SM), 448 threads:
-//   warps 0-7   A producers, one WARP per ring slot (stage it belongs to warp it % STAGES): the 128 neighbour rows x 128 B
-//               of a stage are fetched by 32 TMA tile::gather4 instructions (one per lane, 4 rows each) straight into the
-//               canonical K-major SWIZZLE_128B layout -- the TMA swizzles and zero-fills missing neighbours (index -1 is
-//               out of bounds); lane 0 also pulls the weight slab with ONE cp.async.bulk (weights are stored
+//   warps 0-7   A producers, a WARP per stage (ring slot s belongs to warp s % 8): the valid neighbour rows (x 128 B)
+//               of a stage are fetched by up to 32 TMA tile::gather4 instructions (one per lane, 4 rows each) straight into
+//               the canonical K-major SWIZZLE_128B layout.  MISSING neighbours are not fetched (an out-of-bounds gather row is
+//               zero-filled but costs ~4x an in-bounds one): the stage carries a 128-bit row mask and its MMAs run with those
+//               output lanes disabled.  Lane 0 also pulls the weight slab with ONE cp.async.bulk (weights are stored
 //               pre-swizzled, see gclb_weights_to_tc) onto the same mbarrier.  No LSU traffic, no thread waits for data.
 //   warp  8     issues tcgen05.mma from one elected lane of a warp-uniform loop (descriptors stay in uniform registers);
 //               tcgen05.commit recycles smem slots and publishes accumulators.
-//   warp  9     prefetches the next tile's slice of the neighbour table (cp.async) and lists its populated offsets.
+//   warp  9     prefetches the next tiles' slices of the neighbour table (one bulk copy per tile) and lists their populated offsets.
 //   warps 10-13 epilogue: tcgen05.ld (thread <-> output row), fused scale/shift (+residual) (+ReLU) (+L2 normalise),
-//               overlapped with the next tile's main loop through a double-buffered TMEM accumulator.
+//               overlapped with the next tiles' main loops through a ring of TMEM accumulators, which it hands back zeroed;
+//               output row ids are requested two tiles ahead, residual rows one tile ahead.
 // Every output row is produced by exactly one CTA: no atomics, bit-reproducible.
 // All mbarrier waits are bounded spins that trap on a protocol bug instead of hanging the GPU.
 #include <cuda_fp16.h>
@@ -36,10 +38,15 @@ constexpr int KSLAB = 32;             // tf32: channels per stage = one 128-byte
 // accounting of round 2 (profiles/r02_conv_ablation.md) showed the kernel bound by the serial latency chains of its roles -- one
 // thread issuing a tcgen05.mma every ~100 cycles, barrier round trips, the epilogue of a tile -- not by a throughput resource:
 // with no data movement at all it still took 85 % of its time.  Two CTAs per SM interleave two such chains on the same SM.
+// kEpiWarps: 4 = one epilogue group; 8 = two groups of four warps draining alternate tiles.  Measured (64 -> 64, 641 k rows):
+// two groups with FOUR gather warps lower the per-tile floor (88 -> 76 us at <= 4 offsets per tile) but four warps cannot issue
+// the gathers fast enough (276 instead of 172 ns per stage): 173 us; two groups with EIGHT gather warps (576 threads => 96
+// registers, spills): 129 us; one group, eight gather warps: 125 us.  The code below handles any of these.
 template <int CTAS> struct TcRoles {
   static constexpr int kGatherWarps = CTAS == 2 ? 4 : 8;
+  static constexpr int kEpiWarps = 4;
   static constexpr int kMmaWarp = kGatherWarps, kNbrWarp = kGatherWarps + 1, kEpiWarp0 = kGatherWarps + 2;
-  static constexpr int kThreads = (kGatherWarps + 6) * 32;     // 448 / 320
+  static constexpr int kThreads = (kGatherWarps + 2 + kEpiWarps) * 32;     // 448 / 320
 };
 
 template <int COUT, int MODE = 0, int CTAS = 1>
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
   const uint32_t tmem_base = sh.tmem_base;
   const uint32_t ring_u32 = smem_u32(ring);
   // the row-masked MMAs only ever accumulate: every accumulator starts (and is handed back by the epilogue) as zeros
-  if (warp >= TcRoles<CTAS>::kEpiWarp0) {
+  if (warp >= TcRoles<CTAS>::kEpiWarp0 && warp < TcRoles<CTAS>::kEpiWarp0 + 4) {
     for (int c0 = 0; c0 < Cfg::TMEM_COLS; c0 += 32) tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0);
     tmem_st_wait();
   }
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
       const int* nb = nbr_buf + b * NBR_INTS;
       const int n_iter = sh.n_act[b] * slabs;
       for (int i = 0; i < n_iter; ++i, ++it) {
-        if ((int)(it % S) != warp) continue;              // successive rounds of a slot are ordered => no phase aliasing
+        if ((int)((it % S) % kGatherWarps) != warp) continue;   // a warp walks its slots in stage order => no phase aliasing
         const int k = sh.act_k[b][i / slabs];
         const int c = (i % slabs) * KCH;
         const int stage = it % S;
@@ -180,6 +187,11 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
         }
         __syncwarp();                                        // the barrier is armed before any gather can complete on it
         if ((dbg & 1) || nib == 0u) continue;
+        // every lane issues the gather4 of its own quad.  (A TMA instruction takes its coordinates from uniform registers, so
+        // this compiles to a 32-trip vote loop, ~70 cycles per trip; walking the quads in a warp-uniform loop with shuffled
+        // row ids, four instructions per block on rotating uniform registers, measured SLOWER (85 cycles per instruction).
+        // Eight gather warps reach ~170 ns per 128-row stage, which is also what in-bounds sequential rows reach: the TMA
+        // unit's own rate, ~2.5 cycles per 128-byte row.)
         if (c < p.c0) tma_gather4(a_s + lane * (4 * ROWB), &map0, &sh.full[stage], c, r[0], r[1], r[2], r[3]);
         else tma_gather4(a_s + lane * (4 * ROWB), &map1, &sh.full[stage], c - p.c0, r[0], r[1], r[2], r[3]);
       }
@@ -240,17 +252,38 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
     }
   } else if (warp == kNbrWarp) {
     // ======================================= neighbour-tile prefetch ========================================
+    // Fast path (bucket-sorted table with precomputed tile masks, the engine's case): a whole tile's slice of the table is ONE
+    // bulk copy that completes on nbr_full itself, the populated-offset list comes from the tile mask, and the mask of the next
+    // tile is requested a tile ahead -- this warp never waits for memory, up to NBUF table tiles are in flight.  (Before:
+    // mask load -> cp.async -> wait, one tile at a time: ~1.5 us of exposed latency per tile, the floor of the whole kernel
+    // once the MMA issue chain and the out-of-bounds gathers were gone, profiles/r02_conv_ablation.md.)
+    const bool bulk_ok = !identity && !(p.perm && !nbr_sorted) && p.tile_mask != nullptr &&
+                         (reinterpret_cast<uintptr_t>(p.nbr) & 15u) == 0 && !(dbg & 8);
+    unsigned m_next = (bulk_ok && (int)blockIdx.x < num_tiles) ? __ldg(p.tile_mask + blockIdx.x) : 0u;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int b = lt % NBUF;
+      const unsigned m_cur = m_next;
+      if (bulk_ok && tile + (int)gridDim.x < num_tiles) m_next = __ldg(p.tile_mask + tile + gridDim.x);
       mbar_wait(&sh.nbr_empty[b], ((lt / NBUF) & 1) ^ 1);
       int* nb = nbr_buf + b * NBR_INTS;
+      if (bulk_ok && (int64_t)(tile + 1) * TM <= p.n_out) {
+        if ((m_cur >> lane) & 1u) sh.act_k[b][__popc(m_cur & ((1u << lane) - 1))] = lane;
+        if (lane == 0) sh.n_act[b] = __popc(m_cur);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&sh.nbr_full[b], (uint32_t)NBR_INTS * 4u);
+          bulk_g2s(smem_u32(nb), p.nbr + (int64_t)tile * NBR_INTS, (uint32_t)NBR_INTS * 4u, &sh.nbr_full[b]);
+        }
+        continue;
+      }
       int n_act = 1;
       if (identity) {
         if (lane == 0) sh.act_k[b][0] = 0;
       } else {
         const uint32_t nb_u32 = smem_u32(nb);
-        if (p.perm && !nbr_sorted) {
+        if (dbg & 8) {   // ablation: the neighbour tile is not loaded (combine with bit 0: the indices are garbage)
+        } else if (p.perm && !nbr_sorted) {
           // the table is in its original order: tile row t is table row perm[tile*128 + t].  Each lane fetches its 4
           // rows (27 ints = 108 bytes each, 4-byte aligned) with 4-byte cp.async; rows past the end are zero-filled.
 #pragma unroll
@@ -303,16 +336,21 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
     const int quarter = warp & 3;                      // TMEM lanes this warp may read
     uint32_t amax_bits = 0u;                           // fp16-range monitor: max |y| (float bits; NaN sorts above inf)
     // row ids two tiles ahead, first residual chunk one tile ahead (tc_epilogue.cuh: the epilogue is a per-tile serial chain)
+    constexpr int kGroups = TcRoles<CTAS>::kEpiWarps / 4;         // epilogue groups, each drains every kGroups-th tile of the CTA
+    const int grp = (warp - TcRoles<CTAS>::kEpiWarp0) >> 2;
+    const int64_t g_step = (int64_t)kGroups * gridDim.x;
     EpiState<HALF> est;
-    est.o_cur = epi_row_id(p, blockIdx.x, quarter * 32 + lane, num_tiles);
-    est.o_next = epi_row_id(p, (int64_t)blockIdx.x + gridDim.x, quarter * 32 + lane, num_tiles);
+    est.o_cur = epi_row_id(p, (int64_t)blockIdx.x + (int64_t)grp * gridDim.x, quarter * 32 + lane, num_tiles);
+    est.o_next = epi_row_id(p, (int64_t)blockIdx.x + (int64_t)grp * gridDim.x + g_step, quarter * 32 + lane, num_tiles);
     epi_residual_first<COUT, HALF>(p, est.o_cur, est.rc);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if (lt % kGroups != grp) continue;
       const int ab = lt % NACC;
+      const int64_t t2 = (int64_t)tile + 2 * g_step;
       tc_epilogue_tile<COUT, HALF, false, true, true>(p, tile, quarter, lane, normalize, &sh.acc_full[ab], (lt / NACC) & 1,
                                                       &sh.acc_empty[ab], &sh.acc_n_act[ab], tmem_base + (uint32_t)(ab * COUT),
-                                                      amax_bits, dbg, &est, tile + 2 * (int)gridDim.x, num_tiles);
+                                                      amax_bits, dbg, &est, t2 < num_tiles ? (int)t2 : num_tiles, num_tiles);
     }
     if (p.range_mon) range_mon_flush(p.range_mon, amax_bits);   // saturation / NaN / tiny tensors are reported, never silent
   }
@@ -367,7 +405,8 @@ __global__ void __launch_bounds__(256) weights_to_tc_f16_kernel(const float* __r
 template <int COUT, int KVOL, int MODE, int CTAS>
 static int launch_tc_n(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   using Cfg = TcCfg<COUT, MODE, CTAS>;
-  size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
+  constexpr size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE + (size_t)Cfg::NBUF * TM * KVOL * 4;
+  static_assert(smem + sizeof(TcShared) + 256 <= (CTAS == 2 ? 113u : 227u) * 1024u, "operand ring + neighbour tiles + staging exceed shared memory");
   auto kern = spconv_fwd_tc_kernel<COUT, KVOL, MODE, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -381,7 +420,7 @@ static int launch_tc_n(const ConvParams& p, int64_t n_in, cudaStream_t st) {
   if (rc == GCLB_OK) rc = p.c1 ? make_rows_tensor_map_ex(&map1, p.in1, n_in, p.c1, MODE, false) : (map1 = map0, GCLB_OK);
   if (rc != GCLB_OK) return rc;
   // ablation switches for tools/tileprof.py (WRONG results on purpose): 1 no activation gathers, 2 no weight slabs, 4 no MMAs,
-  // 16 no epilogue math / stores
+  // 8 no neighbour-table loads (use with 1), 16 no epilogue math / stores, 32 no epilogue stores
   static const int dbg = getenv("GCLB_TC_DBG") ? atoi(getenv("GCLB_TC_DBG")) : 0;
   kern<<<grid, TcRoles<CTAS>::kThreads, smem, st>>>(p, num_tiles, (p.relu >> 1) & 1, dbg, map0, map1);
   e = cudaGetLastError();

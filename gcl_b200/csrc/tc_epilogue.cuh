@@ -133,7 +133,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, 
 #pragma unroll
         for (int q = 0; q < 32; ++q) y[q] = y[q] / nrm;
       }
-      if (out_half) {                               // fp16 activations for the next layer (saturating, round to nearest)
+      if (dbg & 32) {                               // ablation: math only (keep it alive through the range monitor)
+#pragma unroll
+        for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
+      } else if (out_half) {                        // fp16 activations for the next layer (saturating, round to nearest)
 #pragma unroll
         for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
         __half* dst = reinterpret_cast<__half*>(p.out) + (size_t)o * COUT + n0;
