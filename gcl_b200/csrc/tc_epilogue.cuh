@@ -101,61 +101,82 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvParams& p, int tile, 
       if (lane == 0) mbar_arrive(acc_empty);
     }
     if (live && !(dbg & 16)) {
+      // ~1000 instructions per thread and tile made the epilogue the tile-rate limit of the narrow layers (profiles/
+      // r02_conv_ablation.md), so the fp16 path is kept lean: no residual arithmetic when there is no residual, ReLU +
+      // saturation + packing in ONE conversion per column pair (cvt.rn[.relu].satfinite.f16x2.f32), the range monitor as a
+      // 3-input NaN-propagating max over pre-saturation magnitudes (16 instead of 64 instructions per 32 columns).
       float y[32];
+      const bool has_res = res != nullptr;
 #pragma unroll
       for (int q = 0; q < 32; q += 4) {
         float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q)) : make_float4(1.f, 1.f, 1.f, 1.f);
         float4 sf = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 r;
-        if constexpr (HALF) {   // 8 halves per 16-byte vector: columns q..q+3 are the low or high half of vector q / 8
-          const float4 raw = rc[q >> 3];
-          const uint32_t w0 = __float_as_uint((q & 4) ? raw.z : raw.x), w1 = __float_as_uint((q & 4) ? raw.w : raw.y);
-          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w0));
-          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w1));
-          r = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          r = rc[q >> 2];
+        // ZERO: an empty tile's accumulator already holds zeros
+        const float a0 = (!ZERO && empty_tile) ? 0.f : __uint_as_float(v[q + 0]), a1 = (!ZERO && empty_tile) ? 0.f : __uint_as_float(v[q + 1]);
+        const float a2 = (!ZERO && empty_tile) ? 0.f : __uint_as_float(v[q + 2]), a3 = (!ZERO && empty_tile) ? 0.f : __uint_as_float(v[q + 3]);
+        y[q + 0] = fmaf(a0, sc.x, sf.x);
+        y[q + 1] = fmaf(a1, sc.y, sf.y);
+        y[q + 2] = fmaf(a2, sc.z, sf.z);
+        y[q + 3] = fmaf(a3, sc.w, sf.w);
+      }
+      if (has_res) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float4 r;
+          if constexpr (HALF) {   // 8 halves per 16-byte vector: columns q..q+3 are the low or high half of vector q / 8
+            const float4 raw = rc[q >> 3];
+            const uint32_t w0 = __float_as_uint((q & 4) ? raw.z : raw.x), w1 = __float_as_uint((q & 4) ? raw.w : raw.y);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+            r = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            r = rc[q >> 2];
+          }
+          y[q + 0] += r.x; y[q + 1] += r.y; y[q + 2] += r.z; y[q + 3] += r.w;
         }
-        y[q + 0] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 0]), sc.x, sf.x) + r.x;
-        y[q + 1] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 1]), sc.y, sf.y) + r.y;
-        y[q + 2] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 2]), sc.z, sf.z) + r.z;
-        y[q + 3] = fmaf(empty_tile ? 0.f : __uint_as_float(v[q + 3]), sc.w, sf.w) + r.w;
       }
-      if (p.relu & 1) {
+      const bool relu = (p.relu & 1) != 0;
+      if (out_half && !(dbg & 32)) {                // fp16 activations for the next layer (saturating, round to nearest)
+        float amax_f = 0.f;
+        uint32_t w[16];
+        if (relu) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) y[q] = fmaxf(y[q], 0.f);
-      }
-      if (COUT == 32 && normalize) {               // F / ||F||_2 per row (model/resunet.py:226-230, no eps)
-        float ss = 0.f;
+          for (int q = 0; q < 32; q += 2) {
+            asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(amax_f) : "f"(y[q]), "f"(y[q + 1]));       // negatives become 0 below
+            asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[q >> 1]) : "f"(y[q + 1]), "f"(y[q]));
+          }
+        } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) ss = fmaf(y[q], y[q], ss);
-        const float nrm = sqrtf(ss);
-#pragma unroll
-        for (int q = 0; q < 32; ++q) y[q] = y[q] / nrm;
-      }
-      if (dbg & 32) {                               // ablation: math only (keep it alive through the range monitor)
-#pragma unroll
-        for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
-      } else if (out_half) {                        // fp16 activations for the next layer (saturating, round to nearest)
-#pragma unroll
-        for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
+          for (int q = 0; q < 32; q += 2) {
+            asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(amax_f) : "f"(fabsf(y[q])), "f"(fabsf(y[q + 1])));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[q >> 1]) : "f"(y[q + 1]), "f"(y[q]));
+          }
+        }
+        amax_bits = max(amax_bits, __float_as_uint(amax_f) & 0x7fffffffu);    // NaN (0x7fffffff) sorts above inf
         __half* dst = reinterpret_cast<__half*>(p.out) + (size_t)o * COUT + n0;
 #pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = fminf(fmaxf(y[q + 2 * j], -65504.f), 65504.f);
-            const float b = fminf(fmaxf(y[q + 2 * j + 1], -65504.f), 65504.f);
-            const __half2 h = __floats2half2_rn(a, b);
-            w[j] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(dst + q) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        for (int q = 0; q < 16; q += 4) *reinterpret_cast<uint4*>(dst + 2 * q) = make_uint4(w[q], w[q + 1], w[q + 2], w[q + 3]);
       } else {
-        float* dst = reinterpret_cast<float*>(p.out) + (size_t)o * COUT + n0;
+        if (relu) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+          for (int q = 0; q < 32; ++q) y[q] = fmaxf(y[q], 0.f);
+        }
+        if (COUT == 32 && normalize) {               // F / ||F||_2 per row (model/resunet.py:226-230, no eps)
+          float ss = 0.f;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) ss = fmaf(y[q], y[q], ss);
+          const float nrm = sqrtf(ss);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) y[q] = y[q] / nrm;
+        }
+        if (dbg & 32) {                             // ablation: math only (kept alive through the range monitor)
+#pragma unroll
+          for (int q = 0; q < 32; ++q) amax_bits = max(amax_bits, __float_as_uint(y[q]) & 0x7fffffffu);
+        } else {
+          float* dst = reinterpret_cast<float*>(p.out) + (size_t)o * COUT + n0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+        }
       }
     }
 #pragma unroll

@@ -19,7 +19,8 @@ def t(fn, reps=10):
   e1.record(); torch.cuda.synchronize()
   return e0.elapsed_time(e1) / reps * 1e3
 order = [13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25, 0, 2, 6, 8, 18, 20, 24, 26]
-for cin, cout in [(64, 64)] if PAIRS != 16 else [(64, 64), (256, 256)]:
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[2:]] or ([(64, 64)] if PAIRS != 16 else [(64, 64), (256, 256)])
+for cin, cout in SHAPES:
   xx = torch.randn(n, cin, device=dev).half()
   W = ops.weights_to_tc(torch.randn(27, cin, cout, device=dev) / 30, half=True)
   res = []
