@@ -262,15 +262,15 @@ class _SparseConvFn(torch.autograd.Function):
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     if ctx.needs_input_grad[0]:
       # mirror: stride-1 odd kernels reuse the forward table with offsets reversed (k -> K-1-k)
-      Wd = (W3.flip(0) if ctx.mirror else W3).transpose(1, 2).contiguous()       # [K, Cout, Cin]
       if ctx.tc_bwd is not None:
-        Wt = ops.weights_to_tc(Wd)
+        Wt = ops.weights_to_tc_dgrad(W3, ctx.mirror)        # flip + transpose + image in one launch
         if ctx.tc_bwd == "mm":
           gx = ops.spconv_fwd(gout, Wt, None, ctx.n_in, algo=2)
         else:
           srt, perm, mask = ctx.tc_bwd
           gx = ops.spconv_fwd(gout, Wt, srt, ctx.n_in, algo=2, row_perm=perm, tile_mask=mask)
       else:
+        Wd = (W3.flip(0) if ctx.mirror else W3).transpose(1, 2).contiguous()       # [K, Cout, Cin]
         gx = ops.spconv_fwd(gout, Wd, ctx.nbr_bwd, ctx.n_in)
     if ctx.needs_input_grad[1]:
       if ctx.tc_fwd is not None and ops.wgrad_tc_supported(x.shape[1], gout.shape[1]):

@@ -48,6 +48,7 @@ SIGNATURES = {
     "gclb_colocation_groups": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i32, C.c_float, C.c_double, _i32, _i32,
                                          _p, _p, _p, _p, _p, _p, _p, _p]),
     "gclb_weights_to_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "gclb_weights_to_tc_dgrad": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "gclb_weights_to_tc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "gclb_spconv_wgrad": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _i32, _p, _p]),
     "gclb_spconv_wgrad_tc": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _p, _i32, _p, _p]),

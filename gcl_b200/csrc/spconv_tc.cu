@@ -366,15 +366,19 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
 // W [K][cin][cout] (ME layout) -> tensor-core image: for every (k, 32-channel slab) one contiguous block of cout x 128 B
 // that is byte-for-byte the SWIZZLE_128B K-major shared-memory tile (row n, 16-byte chunk j at (n/8)*1024 + (n%8)*128 +
 // ((j ^ n%8)*16)), values rounded to nearest-even tf32.  One cp.async.bulk per pipeline stage then stages it.
+// dgrad != 0: (cin, cout) are the DATA-GRADIENT convolution's widths and element (k, c, n) is read from the forward weights
+// Wf [K][cout][cin] at (flip ? K-1-k : k, n, c)
 __global__ void __launch_bounds__(256) weights_to_tc_kernel(const float* __restrict__ W, int K, int cin, int cout,
-                                                            float* __restrict__ Wimg) {
+                                                            float* __restrict__ Wimg, int dgrad, int flip) {
   const int64_t total = (int64_t)K * cin * cout;
   const int slabs = cin / KSLAB;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(e % cout);
-    const int c = (int)((e / cout) % cin);
+    // dgrad: walk the elements with c fastest so that the reads of Wf (cin fastest there) stay coalesced
+    const int n = dgrad ? (int)((e / cin) % cout) : (int)(e % cout);
+    const int c = dgrad ? (int)(e % cin) : (int)((e / cout) % cin);
     const int k = (int)(e / ((int64_t)cout * cin));
-    uint32_t u = __float_as_uint(W[e]);
+    const int64_t src = dgrad ? ((int64_t)(flip ? K - 1 - k : k) * cout + n) * cin + c : e;
+    uint32_t u = __float_as_uint(W[src]);
     u = (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;     // round to nearest even at 10 mantissa bits
     const int sl = c / KSLAB, cc = c % KSLAB, j = cc >> 2, w = cc & 3;
     const int64_t blk = ((int64_t)k * slabs + sl) * ((int64_t)cout * KSLAB);
@@ -497,7 +501,20 @@ int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, flo
   int64_t total = (int64_t)K * cin * cout;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  weights_to_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, Wt);
+  weights_to_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cin, cout, Wt, 0, 0);
+  count_launches(1);
+  GCLB_CHECK_LAUNCH();
+  return GCLB_OK;
+}
+
+int gclb_weights_to_tc_dgrad(const float* W, int32_t K, int32_t cin, int32_t cout, int32_t flip, float* Wt, void* stream) {
+  GCLB_CHECK_ARG(W && Wt && K >= 1 && cin >= 1 && cout >= 1, "bad arguments");
+  GCLB_CHECK_ARG(cout % KSLAB == 0 && cin % 8 == 0, "data-gradient image needs cout % 32 == 0 and cin % 8 == 0");
+  int64_t total = (int64_t)K * cin * cout;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  // the data-gradient convolution maps cout -> cin channels
+  weights_to_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, cout, cin, Wt, 1, flip ? 1 : 0);
   count_launches(1);
   GCLB_CHECK_LAUNCH();
   return GCLB_OK;

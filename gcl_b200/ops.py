@@ -337,6 +337,17 @@ def weights_to_tc(W: torch.Tensor, half: bool = False, c0: Optional[int] = None)
   return Wt
 
 
+def weights_to_tc_dgrad(W: torch.Tensor, flip: bool) -> torch.Tensor:
+  """tf32 tensor-core image of the data-gradient convolution's weights, in one launch from the forward weights
+  [K, Cin, Cout] (or [Cin, Cout]): equals weights_to_tc((W.flip(0) if flip else W).transpose(1, 2))."""
+  require_cuda(W)
+  W3 = (W if W.dim() == 3 else W.unsqueeze(0)).contiguous().float()
+  K, cin, cout = W3.shape
+  Wt = torch.empty((K, cin, cout), dtype=torch.float32, device=W.device)     # image of [K, Cout -> Cin]
+  call("gclb_weights_to_tc_dgrad", ptr(W3), K, cin, cout, int(bool(flip)), ptr(Wt), stream())
+  return Wt
+
+
 def tc_supported(c0: int, c1: int, cout: int, K: int, half: bool = False) -> bool:
   kch = 32
   return (_lib.load().gclb_has_tcgen05() == 1 and c0 % kch == 0 and c1 % kch == 0 and c0 >= kch

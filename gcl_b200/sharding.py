@@ -91,3 +91,35 @@ class FlatGradients:
     else:  # gloo has no AVG
       dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
       self.flat.div_(dist.get_world_size(self.group))
+
+
+class PackedGradients:
+  """Gradient exchange of the data-parallel training step without per-parameter kernels.  `zero()` drops every `.grad`, so
+  autograd hands its gradient tensors over as they are (with a pre-existing `.grad` -- FlatGradients' views -- it launches one
+  add per parameter: 83 launches per step for ResUNetBN2C, ~1 ms of host time in a host-bound step).  `allreduce()` packs the
+  gradients into one flat buffer (one cat), runs ONE all-reduce (AVG) and copies the result back with one multi-tensor copy;
+  with a single rank it does nothing at all."""
+
+  def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+    self.params = [p for p in params if p.requires_grad]
+    self.group = group
+
+  def zero(self):
+    for p in self.params:
+      p.grad = None
+
+  def allreduce(self):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+      return
+    for p in self.params:          # every rank must exchange the same buffer: an unused parameter contributes zeros
+      if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in self.params]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if dist.get_backend(self.group) == "nccl":
+      dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+    else:  # gloo has no AVG
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+      flat.div_(dist.get_world_size(self.group))
+    torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
+

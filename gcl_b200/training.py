@@ -19,7 +19,7 @@ from . import MinkowskiEngine as ME
 from . import groups as gg
 from . import ops, synth
 from .loss import GroupContrastiveLoss
-from .sharding import FlatGradients
+from .sharding import PackedGradients
 
 
 def synthetic_group_batch(rank: int, samples: int, voxel: float = 0.3, sensor=None, seed: int = 0):
@@ -63,7 +63,7 @@ class GclTrainStep:
     self.opt = torch.optim.SGD(self.model.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
     self.crit = GroupContrastiveLoss(pos_thresh=0.1, neg_thresh=1.4, finest_thresh=0.2, square_loss=True,
                                      rng=np.random.default_rng(0))
-    self.grads = FlatGradients(self.model.parameters())
+    self.grads = PackedGradients(self.model.parameters())
 
   def _upload_and_group(self, host_batch, pinned=None):
     """H2D of the clouds, K1 voxelisation of the whole batch, positive groups per sample on the GPU, pair hashes"""

@@ -171,6 +171,11 @@ int gclb_kmap_sort_rows(const int32_t* nbr, int64_t n_out, int32_t ksize, const 
  * cout x 128 B block laid out exactly like the SWIZZLE_128B K-major shared-memory tile, values rounded to nearest tf32
  * (done once per layer; needs cin % 32 == 0, cout % 8 == 0) */
 int gclb_weights_to_tc(const float* W, int32_t K, int32_t cin, int32_t cout, float* Wt, void* stream);
+/* the tf32 image of the DATA-GRADIENT convolution's weights, straight from the forward weights W [K, cin, cout]: the image of
+ * W'[k][c'][n'] = W[flip ? K-1-k : k][n'][c'] (cin' = cout, cout' = cin).  flip = 1 for stride-1 odd kernels, whose backward
+ * table is the forward table with the offsets reversed (lib/colocation_trainer.py:879 `loss.backward()` -> MinkowskiEngine's
+ * ConvolutionBackward; here one launch instead of flip + transpose + copy + image).  Needs cout % 32 == 0, cin % 8 == 0. */
+int gclb_weights_to_tc_dgrad(const float* W, int32_t K, int32_t cin, int32_t cout, int32_t flip, float* Wt, void* stream);
 /* same for the fp16 path: per (k, slab of slab_channels channels) one contiguous block of cout rows of fp16 (round to
  * nearest) -- slab_channels = 64: 128-byte rows, SWIZZLE_128B (flag bit 3 alone); slab_channels = 32: 64-byte rows,
  * SWIZZLE_64B (flag bits 3 + 5).  Wt holds K*cin*cout halves; needs cin % slab_channels == 0, cout % 8 == 0 */

@@ -599,6 +599,19 @@ def test_training_step_grads_vs_oracle(G, mode, w, tol):
     assert _rel(bg.float(), bo.float()) < (1e-5 if mode == "fp32" else tol), k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,cin,cout,flip", [(27, 32, 64, True), (27, 64, 64, False), (8, 128, 64, False), (1, 96, 32, False)])
+def test_dgrad_weight_image_matches_flip_transpose_image(G, K, cin, cout, flip):
+  """gclb_weights_to_tc_dgrad == gclb_weights_to_tc of the flipped / transposed weights (bit-exact: same rounding, same layout)"""
+  if cin % 8 or cout % 32:
+    pytest.skip("shape outside the tensor-core image")
+  torch.manual_seed(K + cin)
+  W = torch.randn(K, cin, cout, device=G.dev)
+  want = G.ops.weights_to_tc((W.flip(0) if flip else W).transpose(1, 2).contiguous())
+  got = G.ops.weights_to_tc_dgrad(W, flip)
+  assert got.shape == want.shape and torch.equal(got, want)
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 32), (64, 64), (32, 64), (128, 128), (256, 256), (256, 64), (64, 128), (128, 256),
                                       (96, 64), (192, 32)])
 def test_wgrad_tc_vs_fp32(G, cin, cout):

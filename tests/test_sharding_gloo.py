@@ -38,6 +38,18 @@ def _worker(rank, world, port, q):
     fg.allreduce()
   for a, b in zip(lin.parameters(), lin2.parameters()):
     assert torch.allclose(a.grad, b.grad)
+  # and through the packed exchange the training step uses now (grads dropped, one cat + one all-reduce + one multi-copy)
+  from gcl_b200.sharding import PackedGradients
+  lin3 = torch.nn.Linear(300, 200)
+  lin3.load_state_dict(lin.state_dict())
+  pg = PackedGradients(lin3.parameters())
+  for _ in range(2):
+    pg.zero()
+    assert all(p.grad is None for p in lin3.parameters())
+    lin3(x).sum().backward()
+    pg.allreduce()
+  for a, b in zip(lin.parameters(), lin3.parameters()):
+    assert torch.allclose(a.grad, b.grad)
   q.put((rank, units, ms, [p.grad.clone() for p in lin.parameters()], local))
   dist.barrier()
   dist.destroy_process_group()
