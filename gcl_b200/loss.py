@@ -160,3 +160,93 @@ class GroupContrastiveLoss:
     pos, _, neg = self._run(F_out, group, index, index_hash, finest_flag, max_pos_cluster, max_hn_samples, False,
                             False, selections, prepared)
     return pos, torch.zeros((), device=F_out.device), neg
+
+  def location_circle_loss(self, F_out, group, index, index_hash, finest_flag, max_pos_cluster=256, max_hn_samples=None,
+                           points=None, batch_lengths=None, block_finest_gradient=True, use_pair_group_positive_loss=False,
+                           log_scale=16, safe_radius=0.75):
+    """The circle-loss head (lib/colocation_trainer.py:538-681; trainer attributes :415-420 as keyword arguments), same call
+    signature and return triple.  Everything runs on F_out's device without a per-group loop: the members of the selected groups
+    are one ragged batch (segment mean / segment log-sum-exp by scatter), the negative term is the dense <= 256 x 256 block the
+    reference builds.  Host work: the reference's RNG calls in the reference's order (group selection, then -- only with
+    use_pair_group_positive_loss -- one `choice(len, 2)` per selected group)."""
+    if not F_out.is_cuda:
+      raise _lib.GclbError("GroupContrastiveLoss runs on CUDA tensors only (no CPU fallback)")
+    if points is None or batch_lengths is None:
+      raise _lib.GclbError("location_circle_loss needs `points` and `batch_lengths` (anchor coordinates / in-batch mask)")
+    dev = F_out.device
+    g_host = np.asarray(group.cpu() if isinstance(group, torch.Tensor) else group, np.int64)
+    G = len(g_host)
+    pos_sel = np.sort(self.rng.choice(G, max_pos_cluster, replace=False)) if G > max_pos_cluster else np.arange(G)
+    S = len(pos_sel)
+    starts = np.concatenate([[0], np.cumsum(g_host)])
+    sizes = g_host[pos_sel]
+    pair = None
+    if use_pair_group_positive_loss:
+      pair = np.stack([self.rng.choice(int(n), 2, replace=False) for n in sizes]).astype(np.int64)      # [S, 2] positions
+    # ragged member list of the selected groups: flat positions into `index`, segment id per member
+    seg_h = np.repeat(np.arange(S), sizes)
+    first_h = starts[pos_sel]
+    flat_h = np.repeat(first_h, sizes) + (np.arange(int(sizes.sum())) - np.repeat(np.cumsum(sizes) - sizes, sizes))
+    seg = torch.from_numpy(seg_h).to(dev)
+    flat = torch.from_numpy(flat_h).to(dev)
+    index_d = torch.as_tensor(index).to(device=dev, dtype=torch.int64)
+    flag_d = torch.as_tensor(finest_flag).to(device=dev, dtype=torch.bool)
+    members = index_d[flat]
+    fl = flag_d[flat]
+    fs = F_out[members]                                                     # [M, C]
+    size_d = torch.from_numpy(sizes).to(dev)
+    mean = torch.zeros((S, F_out.shape[1]), dtype=F_out.dtype, device=dev).index_add_(0, seg, fs) / size_d[:, None].to(F_out.dtype)
+    square = self.square_loss
+
+    def gap(a, b, thr):
+      d2 = (a - b).pow(2).sum(-1)
+      return (d2 if square else torch.sqrt(d2 + 1e-7)) - thr
+
+    def seg_soft_lse(x, sg, n_seg):            # softplus(logsumexp_over_segment(log_scale * x * relu(x).detach())) / log_scale
+      z = log_scale * x * torch.clamp(x, min=0).detach()
+      m = torch.full((n_seg,), -float("inf"), dtype=z.dtype, device=dev).scatter_reduce_(0, sg, z.detach(), reduce="amax")
+      e = torch.zeros((n_seg,), dtype=z.dtype, device=dev).index_add_(0, sg, torch.exp(z - m[sg]))
+      return torch.nn.functional.softplus(torch.log(e) + m) / log_scale
+
+    first_pos = torch.from_numpy(first_h).to(dev)
+    if pair is not None:
+      pa = index_d[first_pos + torch.from_numpy(pair[:, 0]).to(dev)]
+      pb = index_d[first_pos + torch.from_numpy(pair[:, 1]).to(dev)]
+      pos_loss = torch.nn.functional.softplus(gap(F_out[pa], F_out[pb], self.pos_thresh)).sum() / S
+    else:
+      pos_loss = seg_soft_lse(gap(mean[seg], fs, self.pos_thresh / 2), seg, S).sum() / S
+    # first finest member of every selected group
+    pos_in = torch.arange(len(flat_h), device=dev) - torch.repeat_interleave(torch.from_numpy(np.cumsum(sizes) - sizes).to(dev), size_d)
+    big = torch.full((S,), 1 << 30, dtype=torch.int64, device=dev).scatter_reduce_(0, seg[fl], pos_in[fl], reduce="amin")
+    if bool((big >= (1 << 30)).any()):
+      raise _lib.GclbError("location_circle_loss: a selected group has no member with finest_flag set")
+    anchor = F_out[index_d[first_pos + big]]                                # [S, C]
+    if block_finest_gradient:
+      keep = ~fl
+      fin_rows = seg_soft_lse(gap(fs[keep], anchor.detach()[seg[keep]], self.finest_thresh), seg[keep], S)
+    else:
+      fin_rows = seg_soft_lse(gap(fs, anchor[seg], self.finest_thresh), seg, S)
+    finest_loss = fin_rows.sum() / S
+    # negatives: anchors = group means at the coordinates of each group's first member, same batch item only
+    pts = torch.as_tensor(points).to(device=dev, dtype=torch.float32)
+    pivot = index_d[first_pos]
+    coords = pts[pivot]
+    ends = torch.cumsum(torch.as_tensor(np.asarray(batch_lengths, np.float64)), 0).to(dev)
+    bins = (pivot[:, None].to(torch.float64) > ends[None, :]).sum(1)
+    counts = torch.zeros(len(batch_lengths), dtype=torch.int64, device=dev).index_add_(0, bins, torch.ones_like(bins))
+    block = torch.searchsorted(torch.cumsum(counts, 0), torch.arange(S, device=dev), right=True)   # diagonal blocks BY COUNT (:647-652)
+    same_item = block[:, None] == block[None, :]
+
+    def sqdist(x, normalised):
+      d = -2 * x @ x.T
+      d = d + 2 if normalised else d + (x ** 2).sum(-1)[:, None] + (x ** 2).sum(-1)[None, :]
+      return torch.clamp(d, min=1e-12)
+
+    cd = torch.sqrt(sqdist(coords, False))
+    fd = torch.sqrt(sqdist(mean, True))
+    neg_mask = (cd > safe_radius) & same_item
+    has_neg = neg_mask.sum(-1) > 0
+    w = torch.clamp(self.neg_thresh - (fd + 1e5 * (~neg_mask).to(fd.dtype)), min=0).detach()
+    rows = torch.nn.functional.softplus(torch.logsumexp(log_scale * (self.neg_thresh - fd) * w, dim=-1)) / log_scale
+    return pos_loss, finest_loss, rows[has_neg].mean()
+

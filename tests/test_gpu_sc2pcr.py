@@ -171,3 +171,42 @@ def test_hardest_contrastive_loss_vs_reference_golden_and_oracle():
   np.random.seed(7)
   pos2, neg2 = metrics.HardestContrastiveLoss(rng=np.random)(a.detach(), b.detach(), g["pairs"], num_pos=1024, num_hn_samples=512)
   assert abs(pos2.item() - g["losses"][0]) < 1e-5 and abs(neg2.item() - g["losses"][1]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_circle_loss_head_vs_reference_golden_and_oracle():
+  """f4: GroupContrastiveLoss.location_circle_loss (device, no per-group loop) against the reference trainer's own output
+  (tests/golden/circle_loss.npz: values 1e-5, gradients 1e-4 relative) for five settings, and against the oracle on a second
+  seeded draw of the group selection"""
+  import os
+  from gcl_b200.loss import GroupContrastiveLoss
+  from oracle import gcl_loss as oloss
+  dev = torch.device("cuda:0")
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "circle_loss.npz"))
+  variants = {"sq_block": (True, True, False), "sq_open": (True, False, False), "l2_block": (False, True, False),
+              "l2_open": (False, False, False), "sq_pair": (True, True, True)}
+  for name, (square, block, pair) in variants.items():
+    crit = GroupContrastiveLoss(pos_thresh=0.1, neg_thresh=1.4, finest_thresh=0.2, square_loss=square, rng=np.random)
+    F = torch.from_numpy(g["F"]).to(dev).requires_grad_(True)
+    np.random.seed(5)
+    pos, fin, neg = crit.location_circle_loss(F, g["group"], g["index"], None, g["finest_flag"], max_pos_cluster=256,
+                                              points=g["points"], batch_lengths=g["batch_lengths"].tolist(),
+                                              block_finest_gradient=block, use_pair_group_positive_loss=pair)
+    (1.0 * pos + 0.5 * fin + 2.0 * neg).backward()
+    got = np.array([pos.item(), fin.item(), neg.item()])
+    assert np.allclose(got, g[name + "_losses"], rtol=1e-5, atol=1e-6), (name, got, g[name + "_losses"])
+    assert torch.allclose(F.grad.cpu(), torch.from_numpy(g[name + "_grad"]), atol=1e-6, rtol=1e-4), name
+  # a different selection (seed) against the oracle restatement
+  for seed in (1, 2):
+    crit = GroupContrastiveLoss(square_loss=True, rng=np.random)
+    F = torch.from_numpy(g["F"]).to(dev).requires_grad_(True)
+    np.random.seed(seed)
+    out = crit.location_circle_loss(F, g["group"], g["index"], None, g["finest_flag"], max_pos_cluster=200, points=g["points"],
+                                    batch_lengths=g["batch_lengths"].tolist())
+    Fo = torch.from_numpy(g["F"]).clone().requires_grad_(True)
+    np.random.seed(seed)
+    want = oloss.circle_loss(Fo, g["group"], g["index"], g["finest_flag"], g["points"], g["batch_lengths"].tolist(), max_pos_cluster=200)
+    sum(out).backward(); sum(want).backward()
+    assert np.allclose([o.item() for o in out], [w.item() for w in want], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(F.grad.cpu(), Fo.grad, atol=1e-6, rtol=1e-4)
+

@@ -126,3 +126,23 @@ def test_metric_formulas_known_answers():
   assert abs(rte - 0.5) < 1e-6 and abs(np.rad2deg(rre) - 3.0) < 1e-3
   x = torch.randn(100, 3)
   assert omet.evaluate_hit_ratio(x, x @ E[:3, :3].t() + E[:3, 3], E, 0.1) == 1.0
+
+
+CIRCLE_VARIANTS = {"sq_block": (True, True, False), "sq_open": (True, False, False), "l2_block": (False, True, False),
+                   "l2_open": (False, False, False), "sq_pair": (True, True, True)}
+
+
+def test_circle_loss_oracle_vs_reference_golden():
+  """f4, the circle-loss head: oracle/gcl_loss.circle_loss against values + gradients produced by the reference's own
+  FinestContrastiveLossTrainer.location_circle_loss (tests/golden/make_golden_circle.py), five settings"""
+  g = np.load(os.path.join(GOLD, "circle_loss.npz"))
+  for name, (square, block, pair) in CIRCLE_VARIANTS.items():
+    F = torch.from_numpy(g["F"]).clone().requires_grad_(True)
+    np.random.seed(5)
+    pos, fin, neg = oloss.circle_loss(F, g["group"], g["index"], g["finest_flag"], g["points"], g["batch_lengths"].tolist(),
+                                      max_pos_cluster=256, square_loss=square, block_finest_gradient=block,
+                                      use_pair_group_positive_loss=pair)
+    (1.0 * pos + 0.5 * fin + 2.0 * neg).backward()
+    assert np.allclose([pos.item(), fin.item(), neg.item()], g[name + "_losses"], rtol=1e-5, atol=1e-7), name
+    assert torch.allclose(F.grad, torch.from_numpy(g[name + "_grad"]), atol=1e-7, rtol=1e-4), name
+
