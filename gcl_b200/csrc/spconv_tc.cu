@@ -311,8 +311,20 @@ __global__ void __launch_bounds__(TcRoles<CTAS>::kThreads, CTAS) spconv_fwd_tc_k
         __syncwarp();
         const int64_t rows_left = p.n_out - (int64_t)tile * TM;
         const int rows = rows_left < TM ? (int)rows_left : TM;
-        if (rows < TM) {   // rows past the table were zero-filled (= row 0): mark them missing so nothing is gathered
-          for (int e = rows * KVOL + lane; e < NBR_INTS; e += 32) nb[e] = -1;
+        if (rows < TM) {   // rows past the table were zero-filled (= row 0): mark them missing so nothing is gathered.
+          // Every lane patches exactly the words its OWN cp.async wrote (ordered by its own wait above): no cross-lane
+          // write-after-write on the zero-filled chunks
+          if (p.perm && !nbr_sorted) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int t = 4 * lane + q;
+              if (t >= rows) for (int k = 0; k < KVOL; ++k) nb[t * KVOL + k] = -1;
+            }
+          } else {
+            for (int ch = lane; ch < NBR_INTS / 4; ch += 32)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (ch * 4 + j >= rows * KVOL) nb[ch * 4 + j] = -1;
+          }
           __syncwarp();
         }
         if (!p.tile_mask) {   // no precomputed mask: scan the tile (one lane per offset)
