@@ -355,6 +355,7 @@ def main_sweep(args):
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  pin_rank_to_cores(local_rank, world)
   from gcl_b200 import MinkowskiEngine as ME, _lib, synth
   from gcl_b200.engine import ResUNetEngine
   lib = _lib.load()
@@ -438,6 +439,7 @@ def main_train(args):
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  pin_rank_to_cores(local_rank, world)
   from gcl_b200 import _lib
   from gcl_b200.training import GclTrainStep
   lib = _lib.load()
@@ -536,6 +538,24 @@ def main_train(args):
     dist.destroy_process_group()
 
 
+def pin_rank_to_cores(local_rank, world):
+  """N > 1: give every rank its own slice of the host cores this process may use.  A step is ~77 launches issued from one
+  Python thread (~1.6 ms of host work per 3.9 ms step); eight such processes plus their reader threads migrating over the same
+  cores was the round-1 limiter of the 8-GPU run (per-rank step 4.49 -> 4.92 ms with no collective).  GCLB_BENCH_PIN=0 disables."""
+  if world <= 1 or os.environ.get("GCLB_BENCH_PIN", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+    return None
+  try:
+    allowed = sorted(os.sched_getaffinity(0))
+    per = len(allowed) // world
+    if per < 2:
+      return None
+    mine = allowed[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
+  except OSError:
+    return None
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -591,6 +611,7 @@ def main():
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  pin_rank_to_cores(local_rank, world)
   from gcl_b200 import MinkowskiEngine as ME, _lib
   from gcl_b200.pipeline import PairMatcher
   lib = _lib.load()
