@@ -54,3 +54,23 @@ def test_training_workload_reference_arm_and_batch_generator():
   d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
   assert d["impl"] == "reference" and d["metric"] == "gcl_train_scans_per_sec" and d["unit"] == "scans/s" and d["value"] > 0
   assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_weak_scaling_batches_carry_equal_work_on_every_rank():
+  """bench.make_batches: the ranks of a weak-scaling run get the same base scenes under rank-specific poses, so their voxel
+  counts agree to a few % even on a 6-pair batch (0.6 % on the 16-pair batches of the bench; rank-specific scenes differed by +-8 %, which max-over-ranks timing reported as a scaling loss)"""
+  import numpy as np
+  import bench
+  counts = []
+  for rank in range(2):
+    xyz, ptr = bench.make_batches(1, 6, seed=rank)[0]
+    q = np.floor(xyz.numpy() / bench.VOXEL).astype(np.int64)
+    cl = np.repeat(np.arange(len(ptr) - 1), np.diff(ptr.numpy()))
+    key = ((cl * 4096 + q[:, 0] + 2048) * 4096 + q[:, 1] + 2048) * 4096 + q[:, 2] + 2048
+    counts.append(len(np.unique(key)))
+    if rank:
+      assert not np.array_equal(xyz.numpy()[:1000], first[:1000])       # different poses: not the same data
+    else:
+      first = xyz.numpy().copy()
+  assert max(counts) / min(counts) < 1.05, counts
+
