@@ -839,6 +839,35 @@ def main():
                                  "config_KITTI.json), 4x4 transforms read back"},
           "gpu_launches": int(launches), "cuda_mallocs_in_timed_region": [int(new_segments), int(new_segments_e2e)], "clocks": clk,
           "roofline_k1": roof.pop("roofline_k1"), "roofline_k2": roof.pop("roofline_k2"), "roofline": roof}
+  if world == 1 and args.algo == 0 and lib.gclb_has_tcgen05():
+    # the same step at the other two precisions of the engine: tf32 activation storage (tcgen05 kind::tf32, what
+    # the drop-in ME module runs) and exact fp32 (CUDA-core kernels).  Short timed regions: context for the fp16 headline, not
+    # headline numbers themselves.
+    from gcl_b200.engine import ResUNetEngine
+    prec = {}
+    for name, kw in (("tf32_storage_tcgen05", dict(algo=0, half=False)), ("exact_fp32_cuda_core", dict(algo=1))):
+      torch.cuda.empty_cache()
+      m2 = PairMatcher(ResUNetEngine(model, device=dev, **kw), voxel=VOXEL, subsample=SUBSAMPLE, device=dev, seed=rank)
+      def step_p(i):
+        x, p_ = resident[i % n_batches]
+        out = m2.match(x, p_)
+        out["pairs"][:int(out["pair_ptr"].cpu()[-1])].cpu()
+      for i in range(3):
+        step_p(i)
+      torch.cuda.synchronize()
+      n_p = 6 if kw.get("algo") != 1 else 3
+      a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a0.record()
+      for i in range(n_p):
+        step_p(i)
+      a1.record()
+      torch.cuda.synchronize()
+      ms_p = a0.elapsed_time(a1) / n_p
+      prec[name] = {"value": round(args.pairs / (ms_p * 1e-3), 2), "unit": "pairs/s", "ms_per_step": round(ms_p, 3), "steps": n_p}
+      del m2
+    torch.cuda.empty_cache()
+    prec["fp16_storage_tcgen05"] = {"value": round(value, 2), "unit": "pairs/s", "ms_per_step": round(ms / args.steps, 3), "note": "the headline"}
+    line["precisions"] = prec
   if world == 1 and not args.no_cpu_baseline:
     r = run_cpu(steps=5, warmup=1, n_pairs_per_step=1)
     line["cpu_baseline"] = {"value": round(r["pairs_per_s"], 4), "unit": "pairs/s", "cores": r["cores"], "kind": "port",
