@@ -58,7 +58,10 @@ def _worker(rank, world, port, q):
 def test_two_rank_gloo():
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
-  port = 29500 + os.getpid() % 2000
+  import socket
+  with socket.socket() as sk:          # a port that is free right now (a fixed formula can collide with a lingering rendezvous)
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
   procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()
