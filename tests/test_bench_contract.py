@@ -74,3 +74,21 @@ def test_weak_scaling_batches_carry_equal_work_on_every_rank():
       first = xyz.numpy().copy()
   assert max(counts) / min(counts) < 1.05, counts
 
+
+def test_rank_pinning_gives_disjoint_core_slices():
+  """bench.pin_rank_to_cores: one rank is left alone, the ranks of a multi-GPU run get disjoint slices of the allowed cores"""
+  import bench
+  if not hasattr(os, "sched_getaffinity"):
+    return
+  allowed = sorted(os.sched_getaffinity(0))
+  try:
+    assert bench.pin_rank_to_cores(0, 1) is None and sorted(os.sched_getaffinity(0)) == allowed
+    if len(allowed) >= 4:
+      a = bench.pin_rank_to_cores(0, 2)
+      os.sched_setaffinity(0, allowed)
+      b = bench.pin_rank_to_cores(1, 2)
+      assert a and b and not set(a) & set(b) and set(a) | set(b) <= set(allowed)
+      assert sorted(os.sched_getaffinity(0)) == sorted(b)
+  finally:
+    os.sched_setaffinity(0, allowed)
+
